@@ -1,0 +1,123 @@
+"""Seeded input builders shared by tests/golden/make_golden.py (which feeds them to the unmodified
+reference) and by the parity tests (which feed them to the oracle and to the CUDA path).
+Only inputs that cannot be regenerated bit-for-bit from a seed are stored in the fixtures."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mvs_b200 import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+# ---- reference CostRegNet state-dict shapes (probed from the reference modules) ----
+def _cbr_shapes(prefix_conv, prefix_bn, cin, cout, transposed=False):
+    w = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+    return {
+        prefix_conv + ".weight": w,
+        prefix_bn + ".weight": (cout,), prefix_bn + ".bias": (cout,),
+        prefix_bn + ".running_mean": (cout,), prefix_bn + ".running_var": (cout,),
+        prefix_bn + ".num_batches_tracked": (),
+    }
+
+
+def costreg_shapes(family: str, cin: int = 32, base: int = 8) -> dict:
+    s = {}
+    if family in ("mvsnet", "cas"):
+        if family == "mvsnet":
+            cin, base = 32, 8
+        ch = [(cin, base), (base, 2 * base), (2 * base, 2 * base), (2 * base, 4 * base),
+              (4 * base, 4 * base), (4 * base, 8 * base), (8 * base, 8 * base)]
+        for i, (a, b) in enumerate(ch):
+            s.update(_cbr_shapes(f"conv{i}.conv", f"conv{i}.bn", a, b))
+        for name, (a, b) in zip(("conv7", "conv9", "conv11"),
+                                ((8 * base, 4 * base), (4 * base, 2 * base), (2 * base, base))):
+            if family == "mvsnet":
+                s.update(_cbr_shapes(name + ".0", name + ".1", a, b, True))
+            else:
+                s.update(_cbr_shapes(name + ".conv", name + ".bn", a, b, True))
+        s["prob.weight"] = (1, base, 3, 3, 3)
+        if family == "mvsnet":
+            s["prob.bias"] = (1,)
+    elif family == "cvp":
+        for name, (a, b) in (("conv0", (16, 16)), ("conv0a", (16, 16)), ("conv1", (16, 32)),
+                             ("conv2", (32, 32)), ("conv2a", (32, 32)), ("conv3", (32, 64)),
+                             ("conv4", (64, 64)), ("conv4a", (64, 64))):
+            s.update(_cbr_shapes(name + ".conv", name + ".bn", a, b))
+        s.update(_cbr_shapes("conv5.0", "conv5.1", 64, 32, True))
+        s.update(_cbr_shapes("conv6.0", "conv6.1", 32, 16, True))
+        s["prob0.weight"] = (1, 16, 3, 3, 3)
+        s["prob0.bias"] = (1,)
+    else:
+        raise ValueError(family)
+    return s
+
+
+def costreg_state(family: str, cin: int = 32, base: int = 8, seed: int = 0) -> dict:
+    return synth.fill_state_dict(costreg_shapes(family, cin, base), seed)
+
+
+# ---- warp / cost-volume cases -------------------------------------------------------------------
+def warp_plane_case(B=2, C=4, H=24, W=32, D=5, seed=1):
+    fea = synth.features(2, C, H, W, seed, B)
+    proj = synth.proj_matrices(2, W, seed, B)
+    return dict(src_fea=fea[1], ref_fea=fea[0], ref_proj=proj[:, 0], src_proj=proj[:, 1],
+                depth=synth.depth_planes(D, B))
+
+
+def warp_pixel_case(B=2, C=4, H=24, W=32, D=5, seed=2):
+    c = warp_plane_case(B, C, H, W, D, seed)
+    c["depth"] = synth.depth_per_pixel(D, H, W, interval=21.25, batch=B)
+    return c
+
+
+def volume_case(n_views=4, B=1, C=8, H=16, W=24, D=8, seed=3, per_pixel=False):
+    fea = synth.features(n_views, C, H, W, seed, B)
+    proj = synth.proj_matrices(n_views, W, seed, B)
+    depth = synth.depth_per_pixel(D, H, W, 10.6, B) if per_pixel else synth.depth_planes(D, B)
+    return dict(feats=fea, proj=proj, depth=depth)
+
+
+def cas_case(n_views=3, B=1, C=16, H=16, W=24, D=8, seed=4, per_pixel=True):
+    fea = synth.features(n_views, C, H, W, seed, B)
+    proj = synth.cas_proj_matrices(n_views, W, seed, B)
+    depth = synth.depth_per_pixel(D, H, W, 10.6, B) if per_pixel else synth.depth_planes(D, B)
+    return dict(feats=fea, proj=proj, depth=depth)
+
+
+def cascade_case(n_views=3, B=1, H=64, W=96, ndepths=(16, 8, 8), seed=5):
+    """Full 3-stage CasMVSNet from FPN-shaped features: stage k features [C_k, H/s_k, W/s_k]."""
+    chans = (32, 16, 8)
+    scales = (4, 2, 1)
+    feats = {}
+    projs = {}
+    for i, (c, s) in enumerate(zip(chans, scales)):
+        feats[f"stage{i + 1}"] = synth.features(n_views, c, H // s, W // s, seed + i, B)
+        projs[f"stage{i + 1}"] = synth.cas_proj_matrices(n_views, W // s, seed, B)
+    depth_values = synth.depth_planes(192, B)  # the dataset hands 192 planes; only [0] and [-1] are used
+    return dict(feats=feats, projs=projs, depth_values=depth_values, ndepths=list(ndepths), H=H, W=W)
+
+
+def cvp_case(n_src=2, B=1, C=16, H=16, W=24, D=8, seed=6, per_pixel=True):
+    fea = synth.features(n_src + 1, C, H, W, seed, B)
+    ref_in, src_in, ref_ex, src_ex = synth.cvp_cameras(n_src, W, seed, B)
+    depth = synth.depth_per_pixel(D, H, W, 10.6, B) if per_pixel else synth.depth_planes(D, B)
+    return dict(feats=fea, ref_in=ref_in, src_in=src_in, ref_ex=ref_ex, src_ex=src_ex, depth=depth)
+
+
+def logits_case(B=2, D=12, H=10, W=14, seed=7, per_pixel=False):
+    rng = np.random.RandomState(4000 + seed)
+    logits = (3.0 * rng.standard_normal((B, D, H, W))).astype(np.float32)
+    depth = synth.depth_per_pixel(D, H, W, 10.6, B) if per_pixel else synth.depth_planes(D, B)
+    return dict(logits=logits, depth=depth)
