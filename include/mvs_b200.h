@@ -1,0 +1,160 @@
+/*
+ * mvs_b200.h -- C ABI of the B200-native MVSNet-family cost-volume hot path.
+ *
+ * The reference (doubleZ0108/MVS) has no FFI / plugin registry for this path: its boundary is a set
+ * of Python callables in each project's models/module(s).py.  This header is the
+ * C-ABI a maintainer would bind behind those callables; every entry point cites the reference
+ * interface it replaces.  INTEGRATION.md shows the ctypes binding and the `patch_reference` hook.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller (torch owns the memory) unless
+ *     the parameter name ends in `_host`; nothing is allocated or retained inside the library;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     all work is enqueued on it and the call returns without synchronising;
+ *   - return value: MVS_OK (0) or a negative MVS_ERR_* code; mvs_last_error() gives the message
+ *     for the calling thread.  No global mutable state => re-entrant across threads / streams;
+ *   - "NCHW"/"NCDHW" are the reference's contiguous fp32 layouts.  "C8" is this library's fast
+ *     layout: channels blocked by 8, [B][C/8][D][H][W][8] bf16 (16 B per voxel per block), see
+ *     DESIGN.md "Data layout in HBM".
+ *   - rot [B,nsrc,9] / trans [B,nsrc,3]: rows of proj[:, :3, :3] and proj[:, :3, 3] where
+ *     proj = src_proj @ inverse(ref_proj) (MVSNet/models/module.py:63-65), fp32, computed by the
+ *     caller with torch so that both sides of every parity test consume identical bits.
+ */
+#ifndef MVS_B200_H
+#define MVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVS_OK 0
+#define MVS_ERR_INVALID (-1)      /* bad argument (shape, null pointer, unsupported combination) */
+#define MVS_ERR_CUDA (-2)         /* a CUDA runtime / driver call failed                          */
+#define MVS_ERR_UNSUPPORTED (-3)  /* valid request this build cannot serve                        */
+
+/* flags (bit-or) */
+#define MVS_ALIGN_CORNERS 1     /* grid_sample(align_corners=True): MVSNet_pl/models/modules.py:57-59 */
+#define MVS_PL_ORDER 2          /* MVSNet_pl op order R@(xyz*d)+T: MVSNet_pl/models/modules.py:46-50  */
+#define MVS_REF_SUM_SQUARED 4   /* CVP aliasing quirk: CVP-MVSNet/models/net.py:129-130, modules.py:228-229 */
+#define MVS_RELU 8              /* conv epilogue: apply ReLU after the affine                    */
+#define MVS_CLAMP_INDEX 16      /* CasMVSNet/models/cas_mvsnet.py:62 depth_index.clamp(0, D-1)    */
+#define MVS_INPUT_IS_PROB 32    /* softargmin: input already soft-maxed (depth_regression(p, d)) */
+
+/* depth_mode */
+#define MVS_DEPTH_PLANE 0       /* depth [B,D]       MVSNet/models/module.py:46                   */
+#define MVS_DEPTH_PIXEL 1       /* depth [B,D,H,W]   CasMVSNet/models/module.py:245,267-268        */
+
+/* dtype */
+#define MVS_F32 0
+#define MVS_BF16 1
+
+#define MVS_MAX_SRC 8           /* source views the fused builder takes in one launch            */
+
+int mvs_version(void);
+int mvs_sm(void);                         /* architecture the kernels were compiled for (100)    */
+const char *mvs_last_error(void);         /* thread-local, never NULL                            */
+int64_t mvs_launch_count(void);           /* kernels launched by this library since load         */
+
+/* ---- a1: homography warp --------------------------------------------------------------------
+ * Replaces homo_warping(src_fea, src_proj, ref_proj, depth_values) -> [B,C,D,H,W]
+ *   MVSNet/models/module.py:46-87, CasMVSNet/models/module.py:245-280,
+ *   CVP-MVSNet/models/modules.py:81-119, and homo_warp: MVSNet_pl/models/modules.py:25-62
+ *   (flags = MVS_ALIGN_CORNERS|MVS_PL_ORDER).  src_fea NCHW fp32, rot [B,9], trans [B,3],
+ *   out NCDHW fp32.  Bit-exact with the reference's CPU path. */
+int mvs_warp_fwd(const float *src_fea, const float *rot, const float *trans, const float *depth,
+                 int depth_mode, float *out, int B, int C, int D, int H, int W, int flags,
+                 void *stream);
+
+/* Backward of mvs_warp_fwd w.r.t. src_fea (the grid is built under no_grad, module.py:62):
+ * grad_src[b,c,tap] += grad_out[b,c,d,y,x] * w_tap.  grad_src is a caller-zeroed NCHW fp32 buffer. */
+int mvs_warp_bwd(const float *grad_out, const float *rot, const float *trans, const float *depth,
+                 int depth_mode, float *grad_src, int B, int C, int D, int H, int W, int flags,
+                 void *stream);
+
+/* Integer bilinear tap indices of the same warp (floor(ix), floor(iy) saturated to int32) and the
+ * 4-bit in-bounds mask (bit0 nw, bit1 ne, bit2 sw, bit3 se); ixy (optional) receives the fp32
+ * sample position.  All [B,D,H,W] (ixy: [B,D,H,W,2]).  Used to prove index parity. */
+int mvs_warp_taps(const float *rot, const float *trans, const float *depth, int depth_mode,
+                  int32_t *x0, int32_t *y0, uint8_t *mask, float *ixy, int B, int D, int H, int W,
+                  int flags, void *stream);
+
+/* ---- a1+a2 fused: warp of every source view + variance over views, volume written once -------
+ * Replaces the builder loops MVSNet/models/mvsnet.py:152-170, CasMVSNet/models/cas_mvsnet.py:24-46,
+ * CVP-MVSNet/models/net.py:127-152 and proj_cost modules.py:221-275 (MVS_REF_SUM_SQUARED).
+ * srcs_host: HOST array of nsrc (<= MVS_MAX_SRC) device pointers, each [B,C,H,W] like ref.
+ * Strict variant: fp32 NCHW in, fp32 NCDHW out, bit-exact with the reference's CPU path. */
+int mvs_warp_variance_fwd(const float *ref, const float *const *srcs_host, int nsrc,
+                          const float *rot, const float *trans, const float *depth, int depth_mode,
+                          float *out, int B, int C, int D, int H, int W, int flags, void *stream);
+
+/* Backward of the builder w.r.t. the feature maps (the grid is built under no_grad in the
+ * reference, module.py:62).  grad_out NCDHW fp32; grad_ref / grad_srcs accumulate (+=) into
+ * caller-zeroed NCHW fp32 buffers. */
+int mvs_warp_variance_bwd(const float *grad_out, const float *ref, const float *const *srcs_host,
+                          int nsrc, const float *rot, const float *trans, const float *depth,
+                          int depth_mode, float *grad_ref, float *const *grad_srcs_host, int B, int C,
+                          int D, int H, int W, int flags, void *stream);
+
+/* Fast variant: C8 bf16 feature maps in ([B][C/8][H][W][8]), C8 bf16 volume out
+ * ([B][C/8][D][H][W][8]); fp32 coordinates (same tap indices as the strict path), fp32 blend and
+ * accumulation, one bf16 rounding at the store.  C % 8 == 0. */
+int mvs_warp_variance_c8_fwd(const void *ref_c8, const void *const *srcs_c8_host, int nsrc,
+                             const float *rot, const float *trans, const float *depth,
+                             int depth_mode, void *out_c8, int B, int C, int D, int H, int W,
+                             int flags, void *stream);
+
+/* ---- layout hand-off ----------------------------------------------------
+ * NC(D)HW (fp32 or bf16) <-> C8 bf16.  `inner` = D*H*W (or H*W).  C is zero-padded up to a
+ * multiple of 8 on pack; unpack drops the padding. */
+int mvs_pack_c8(const void *src, int src_dtype, void *dst_c8, int B, int C, int64_t inner, void *stream);
+int mvs_unpack_c8(const void *src_c8, void *dst, int dst_dtype, int B, int C, int64_t inner, void *stream);
+
+/* ---- a3: 3x3x3 convolution + folded BatchNorm + ReLU + skip ------------------------------------
+ * Replaces ConvBnReLU3D / Conv3d / Deconv3d blocks and the skip adds of CostRegNet.forward:
+ *   MVSNet/models/module.py:26-33, mvsnet.py:55-93; CasMVSNet/models/module.py:115-200,407-438;
+ *   CVP-MVSNet/models/net.py:52-89.
+ * y = [skip +] act( conv(x, w) * scale[co] + shift[co] ),  kernel 3, padding 1.
+ *   transposed = 0: weight [Cout,Cin,3,3,3], out extent = (n-1)/stride+1
+ *   transposed = 1: ConvTranspose3d(stride, padding=1, output_padding=stride-1), weight
+ *                   [Cin,Cout,3,3,3], out extent = n*stride
+ * scale/shift may be NULL (identity / zero); skip has the output's shape.  D,H,W are INPUT extents.
+ * Strict variant: fp32 NCDHW, fp32 FMA accumulation. */
+int mvs_conv3d_fwd(const float *x, const float *w, const float *scale, const float *shift,
+                   const float *skip, float *y, int B, int Cin, int Cout, int D, int H, int W,
+                   int stride, int transposed, int flags, void *stream);
+
+/* Fast variant: C8 bf16 activations, tcgen05 (UMMA) implicit GEMM with TMA-staged bricks and a
+ * TMEM accumulator; weights pre-packed by mvs_conv3d_c8_pack_weights.  y is C8 bf16, or fp32
+ * [B,D,H,W] when Cout == 1 (the `prob` layer). */
+int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stride, int transposed);
+int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride,
+                               int transposed, void *stream);
+int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const float *scale, const float *shift,
+                      const void *skip_c8, void *y, int B, int Cin, int Cout, int D, int H, int W,
+                      int stride, int transposed, int flags, void *stream);
+
+/* ---- a4+a5+a6: softmax over D + soft-argmin depth + photometric confidence ---------------------
+ * Replaces F.softmax(cost_reg, 1) + depth_regression + the pad/avg_pool3d/gather confidence:
+ *   MVSNet/models/mvsnet.py:183-191, module.py:91-103; CasMVSNet/models/cas_mvsnet.py:51-64
+ *   (MVS_CLAMP_INDEX); CVP-MVSNet/models/net.py:162-163,185-199, modules.py:338-355.
+ * logits [B,D,H,W] fp32; depth [B,D] or [B,D,H,W]; out_depth, out_conf [B,H,W] fp32;
+ * out_prob [B,D,H,W] (optional), out_index int32 [B,H,W] (optional). */
+int mvs_softargmin_conf_fwd(const float *logits, const float *depth, int depth_mode,
+                            float *out_depth, float *out_conf, float *out_prob, int32_t *out_index,
+                            int B, int D, int H, int W, int flags, void *stream);
+
+/* ---- f2: depth-hypothesis generation (the step before the path) -------------------------------
+ * Replaces get_depth_range_samples (per-pixel branch) CasMVSNet/models/module.py:485-524:
+ * out[b,k,y,x] = (cur - D/2*interval) + k * ((cur + D/2*interval) - (cur - D/2*interval))/(D-1).
+ * `interval` is the Python double depth_inteval_pixel; D/2*interval is formed in double and cast to
+ * fp32 once, like the reference's tensor-minus-scalar.  cur [B,H,W] fp32 -> out [B,D,H,W] fp32,
+ * bit-exact with the reference's CPU path. */
+int mvs_depth_range_samples(const float *cur, double interval, int ndepth, float *out, int B, int H,
+                            int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVS_B200_H */

@@ -1,0 +1,81 @@
+"""ctypes loader for the C-ABI library (include/mvs_b200.h -> mvs_b200/libmvs_b200.so).
+
+There is NO fallback: if the library is missing or a call fails, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvs_b200.so")
+
+# flags / enums (mirror include/mvs_b200.h)
+ALIGN_CORNERS = 1
+PL_ORDER = 2
+REF_SUM_SQUARED = 4
+RELU = 8
+CLAMP_INDEX = 16
+INPUT_IS_PROB = 32
+DEPTH_PLANE = 0
+DEPTH_PIXEL = 1
+F32 = 0
+BF16 = 1
+MAX_SRC = 8
+
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+# name -> (restype, argtypes); the single source of truth the symbol test checks against the header
+SIGNATURES = {
+    "mvs_version": (_i, []),
+    "mvs_sm": (_i, []),
+    "mvs_last_error": (C.c_char_p, []),
+    "mvs_launch_count": (_i64, []),
+    "mvs_warp_fwd": (_i, [_vp] * 4 + [_i, _vp] + [_i] * 6 + [_vp]),
+    "mvs_warp_bwd": (_i, [_vp] * 4 + [_i, _vp] + [_i] * 6 + [_vp]),
+    "mvs_warp_taps": (_i, [_vp] * 3 + [_i] + [_vp] * 4 + [_i] * 5 + [_vp]),
+    "mvs_warp_variance_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp] + [_i] * 6 + [_vp]),
+    "mvs_warp_variance_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp] + [_i] * 6 + [_vp]),
+    "mvs_warp_variance_c8_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp] + [_i] * 6 + [_vp]),
+    "mvs_pack_c8": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
+    "mvs_unpack_c8": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp]),
+    "mvs_conv3d_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
+    "mvs_conv3d_c8_packed_weight_bytes": (_i64, [_i] * 4),
+    "mvs_conv3d_c8_pack_weights": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
+    "mvs_conv3d_c8_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
+    "mvs_softargmin_conf_fwd": (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i] * 5 + [_vp]),
+    "mvs_depth_range_samples": (_i, [_vp, _d, _i, _vp, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+class MvsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the CDLL; raises MvsError when the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MvsError(
+                f"{LIB_PATH} is missing: build it with `python -m mvs_b200.csrc.build` "
+                "(__graft_entry__.build()).  mvs_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = lib().mvs_last_error().decode("utf-8", "replace")
+        raise MvsError(f"{what} failed ({code}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().mvs_launch_count())

@@ -1,0 +1,67 @@
+"""Builds mvs_b200/libmvs_b200.so from the .cu sources in this directory with nvcc for sm_100a.
+
+    python -m mvs_b200.csrc.build [--force] [--verbose]
+
+The library is built IN-TREE (it travels to the GPU box with the repo snapshot) and links cudart
+statically, so loading it needs no CUDA driver: the symbol test runs in the GPU-less container.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT = os.path.join(PKG, "libmvs_b200.so")
+OBJ_DIR = os.path.join(HERE, "build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DMVS_TARGET_SM=100",
+          "--expt-relaxed-constexpr"]
+
+
+def sources():
+    return sorted(f for f in os.listdir(HERE) if f.endswith(".cu"))
+
+
+def headers_mtime():
+    hs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    hs.append(os.path.join(os.path.dirname(PKG), "include", "mvs_b200.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def compile_one(src, force, verbose):
+    obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+    spath = os.path.join(HERE, src)
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(spath), headers_mtime()):
+        return obj, ""
+    cmd = [NVCC, *ARCH, *CFLAGS, "-c", spath, "-o", obj]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")
+    with open(obj + ".ptxas.log", "w") as f:
+        f.write(p.stderr)
+    return obj, p.stderr if verbose else ""
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    srcs = sources()
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        res = list(ex.map(lambda s: compile_one(s, force, verbose), srcs))
+    objs = [r[0] for r in res]
+    if verbose:
+        for _, log in res:
+            sys.stderr.write(log)
+    if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
+        cmd = [NVCC, *ARCH, "-shared", "-o", OUT, *objs, "-cudart", "static", "-Xcompiler", "-fPIC"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build("--force" in sys.argv, "--verbose" in sys.argv))

@@ -1,0 +1,290 @@
+"""nn.Module mirrors of the reference's hot-path classes, running on the sm_100a kernels.
+
+State-dict compatibility is part of the drop-in boundary: every class below builds
+the same sub-module tree as its reference counterpart (plain nn.Conv3d / ConvTranspose3d /
+BatchNorm3d used as PARAMETER HOLDERS, never called), so a reference checkpoint loads with
+``strict=True``.  forward() folds eval-mode BatchNorm into a per-channel (scale, shift) pair and runs
+every layer as one fused conv + affine + ReLU (+ skip) kernel.
+
+Precision modes
+  "strict": fp32 NCDHW end to end (parity mode: tracks the reference's fp32 CPU path).
+  "fast":   bf16 C8 activations on the tcgen05 tensor cores (throughput mode).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import _lib as L
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders with the reference's names
+# ------------------------------------------------------------------------------------------------
+class ConvBnReLU3D(nn.Module):
+    """Keys ``conv.weight, bn.*`` -- MVSNet/models/module.py:26-33, CVP-MVSNet/models/modules.py."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, pad=1):
+        super().__init__()
+        assert kernel_size == 3 and pad == 1, "the hot path only has 3x3x3 / pad 1 convolutions"
+        self.conv = nn.Conv3d(in_channels, out_channels, 3, stride=stride, padding=1, bias=False)
+        self.bn = nn.BatchNorm3d(out_channels)
+        self.stride, self.transposed = stride, False
+
+    def forward(self, x, skip=None, mode="strict"):
+        return _run_layer(x, self.conv.weight, self.bn, self.stride, False, True, skip, mode, self)
+
+
+class Conv3d(nn.Module):
+    """Keys ``conv.weight, bn.*`` -- CasMVSNet/models/module.py:115-157 (bn momentum 0.1)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        assert kernel_size == 3 and kwargs.get("padding", 1) == 1 and stride in (1, 2) and bn
+        self.conv = nn.Conv3d(in_channels, out_channels, 3, stride=stride, bias=False, padding=1)
+        self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum)
+        self.stride, self.relu = stride, relu
+
+    def forward(self, x, skip=None, mode="strict"):
+        return _run_layer(x, self.conv.weight, self.bn, self.stride, False, self.relu, skip, mode, self)
+
+
+class Deconv3d(nn.Module):
+    """Keys ``conv.weight, bn.*`` -- CasMVSNet/models/module.py:159-200."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        assert kernel_size == 3 and kwargs.get("padding", 1) == 1 and stride in (1, 2) and bn
+        assert kwargs.get("output_padding", 0) == stride - 1
+        self.conv = nn.ConvTranspose3d(in_channels, out_channels, 3, stride=stride, bias=False, padding=1,
+                                       output_padding=stride - 1)
+        self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum)
+        self.stride, self.relu = stride, relu
+
+    def forward(self, x, skip=None, mode="strict"):
+        return _run_layer(x, self.conv.weight, self.bn, self.stride, True, self.relu, skip, mode, self)
+
+
+def _deconv_seq(cin, cout, stride):
+    """nn.Sequential(ConvTranspose3d, BatchNorm3d, ReLU): keys ``0.weight, 1.*`` (mvsnet.py:65-78)."""
+    return nn.Sequential(
+        nn.ConvTranspose3d(cin, cout, kernel_size=3, padding=1, output_padding=stride - 1, stride=stride, bias=False),
+        nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
+
+
+def _fold_bn(bn: Optional[nn.BatchNorm3d], cache_owner: nn.Module):
+    """Eval-mode BN -> (scale, shift) fp32, cached until any BN tensor is modified in place or replaced."""
+    if bn is None:
+        return None, None
+    key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+    cached = getattr(cache_owner, "_mvs_fold", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    with torch.no_grad():
+        scale = (bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps))
+        shift = bn.bias.double() - bn.running_mean.double() * scale
+        scale, shift = scale.float().contiguous(), shift.float().contiguous()
+    cache_owner._mvs_fold = (key, scale, shift)
+    return scale, shift
+
+
+def _run_layer(x, weight, bn, stride, transposed, relu, skip, mode, owner):
+    if owner.training and bn is not None:
+        raise NotImplementedError(
+            "mvs_b200 CostRegNet: training-mode BatchNorm (batch statistics) is not built yet; "
+            "call .eval() (inference) -- see DESIGN.md 'out of scope this round'")
+    scale, shift = _fold_bn(bn, owner)
+    if mode == "strict":
+        return ops.conv3d(x, weight, scale, shift, skip, stride, transposed, relu)
+    raise L.MvsError(f"CostRegNet mode {mode!r}: only 'strict' is wired up in this revision")
+
+
+def _seq_layer(seq: nn.Sequential, x, skip, mode):
+    return _run_layer(x, seq[0].weight, seq[1], seq[0].stride[0], True, True, skip, mode, seq)
+
+
+# ------------------------------------------------------------------------------------------------
+# the three CostRegNet topologies
+# ------------------------------------------------------------------------------------------------
+class CostRegNetMVSNet(nn.Module):
+    """MVSNet/models/mvsnet.py:48-93: 32->8->16(s2)->16->32(s2)->32->64(s2)->64, three stride-2
+    transposed convs with skip adds, prob conv with bias.  [B,32,D,h,w] -> [B,1,D,h,w]."""
+
+    def __init__(self, mode="strict"):
+        super().__init__()
+        self.mode = mode
+        self.conv0 = ConvBnReLU3D(32, 8)
+        self.conv1 = ConvBnReLU3D(8, 16, stride=2)
+        self.conv2 = ConvBnReLU3D(16, 16)
+        self.conv3 = ConvBnReLU3D(16, 32, stride=2)
+        self.conv4 = ConvBnReLU3D(32, 32)
+        self.conv5 = ConvBnReLU3D(32, 64, stride=2)
+        self.conv6 = ConvBnReLU3D(64, 64)
+        self.conv7 = _deconv_seq(64, 32, 2)
+        self.conv9 = _deconv_seq(32, 16, 2)
+        self.conv11 = _deconv_seq(16, 8, 2)
+        self.prob = nn.Conv3d(8, 1, 3, stride=1, padding=1)
+
+    def forward(self, x):
+        m = self.mode
+        _check_divisible(x, 8)
+        conv0 = self.conv0(x, mode=m)
+        conv2 = self.conv2(self.conv1(conv0, mode=m), mode=m)
+        conv4 = self.conv4(self.conv3(conv2, mode=m), mode=m)
+        x = self.conv6(self.conv5(conv4, mode=m), mode=m)
+        x = _seq_layer(self.conv7, x, conv4, m)
+        x = _seq_layer(self.conv9, x, conv2, m)
+        x = _seq_layer(self.conv11, x, conv0, m)
+        return _prob_layer(self.prob, x, m)
+
+
+class CostRegNetCas(nn.Module):
+    """CasMVSNet/models/module.py:407-438: same topology, parametrised (in_channels, base_channels),
+    Conv3d/Deconv3d blocks (keys convN.conv / convN.bn), prob without bias."""
+
+    def __init__(self, in_channels, base_channels, mode="strict"):
+        super().__init__()
+        self.mode = mode
+        b = base_channels
+        self.conv0 = Conv3d(in_channels, b, padding=1)
+        self.conv1 = Conv3d(b, b * 2, stride=2, padding=1)
+        self.conv2 = Conv3d(b * 2, b * 2, padding=1)
+        self.conv3 = Conv3d(b * 2, b * 4, stride=2, padding=1)
+        self.conv4 = Conv3d(b * 4, b * 4, padding=1)
+        self.conv5 = Conv3d(b * 4, b * 8, stride=2, padding=1)
+        self.conv6 = Conv3d(b * 8, b * 8, padding=1)
+        self.conv7 = Deconv3d(b * 8, b * 4, stride=2, padding=1, output_padding=1)
+        self.conv9 = Deconv3d(b * 4, b * 2, stride=2, padding=1, output_padding=1)
+        self.conv11 = Deconv3d(b * 2, b * 1, stride=2, padding=1, output_padding=1)
+        self.prob = nn.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
+
+    def forward(self, x):
+        m = self.mode
+        _check_divisible(x, 8)
+        conv0 = self.conv0(x, mode=m)
+        conv2 = self.conv2(self.conv1(conv0, mode=m), mode=m)
+        conv4 = self.conv4(self.conv3(conv2, mode=m), mode=m)
+        x = self.conv6(self.conv5(conv4, mode=m), mode=m)
+        x = self.conv7(x, skip=conv4, mode=m)
+        x = self.conv9(x, skip=conv2, mode=m)
+        x = self.conv11(x, skip=conv0, mode=m)
+        return _prob_layer(self.prob, x, m)
+
+
+class CostRegNetCVP(nn.Module):
+    """CVP-MVSNet/models/net.py:52-89: 16->16->16 | 32(s2)->32->32->64->64->64 | deconv s1 64->32
+    (+conv2) | deconv s2 32->16 (+conv0) | prob0 16->1 (bias); returns the squeezed [B,D,h,w]."""
+
+    def __init__(self, mode="strict"):
+        super().__init__()
+        self.mode = mode
+        self.conv0 = ConvBnReLU3D(16, 16)
+        self.conv0a = ConvBnReLU3D(16, 16)
+        self.conv1 = ConvBnReLU3D(16, 32, stride=2)
+        self.conv2 = ConvBnReLU3D(32, 32)
+        self.conv2a = ConvBnReLU3D(32, 32)
+        self.conv3 = ConvBnReLU3D(32, 64)
+        self.conv4 = ConvBnReLU3D(64, 64)
+        self.conv4a = ConvBnReLU3D(64, 64)
+        self.conv5 = _deconv_seq(64, 32, 1)
+        self.conv6 = _deconv_seq(32, 16, 2)
+        self.prob0 = nn.Conv3d(16, 1, 3, stride=1, padding=1)
+
+    def forward(self, x):
+        m = self.mode
+        _check_divisible(x, 2)
+        conv0 = self.conv0a(self.conv0(x, mode=m), mode=m)
+        conv2 = self.conv2a(self.conv2(self.conv1(conv0, mode=m), mode=m), mode=m)
+        conv4 = self.conv4a(self.conv4(self.conv3(conv2, mode=m), mode=m), mode=m)
+        conv5 = _seq_layer(self.conv5, conv4, conv2, m)
+        conv6 = _seq_layer(self.conv6, conv5, conv0, m)
+        return _prob_layer(self.prob0, conv6, m).squeeze(1)
+
+
+def _check_divisible(x, k):
+    if any(s % k for s in x.shape[2:]):
+        raise ValueError(f"CostRegNet needs D,H,W divisible by {k} for its skip adds "
+                         f"(the reference fails at the add, mvsnet.py:89-91); got {tuple(x.shape[2:])}")
+
+
+def _prob_layer(conv: nn.Conv3d, x, mode):
+    shift = conv.bias.detach().float() if conv.bias is not None else None
+    if mode == "strict":
+        return ops.conv3d(x, conv.weight, None, shift, None, 1, False, False)
+    raise L.MvsError(f"CostRegNet mode {mode!r}: only 'strict' is wired up in this revision")
+
+
+def CostRegNet(*args, **kwargs):
+    """Reference-compatible constructor: ``CostRegNet()`` -> MVSNet topology (mvsnet.py:48),
+    ``CostRegNet(in_channels, base_channels)`` -> CasMVSNet topology (module.py:407)."""
+    if not args and "in_channels" not in kwargs:
+        return CostRegNetMVSNet(**kwargs)
+    return CostRegNetCas(*args, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# builders + per-stage forward ("DepthNet")
+# ------------------------------------------------------------------------------------------------
+def build_cost_volume(ref_fea, src_feas: Sequence[torch.Tensor], ref_proj, src_projs: Sequence[torch.Tensor],
+                      depth_values, flags: int = 0):
+    """Fused replacement of the builder loop (MVSNet/models/mvsnet.py:152-170): the N-1 warped
+    volumes are never materialised.  Projections are the reference's fused 4x4 matrices."""
+    rots, transs = zip(*(ops.relative_pose(sp, ref_proj) for sp in src_projs))
+    return ops.cost_volume(ref_fea, list(src_feas), list(rots), list(transs), depth_values, flags)
+
+
+def regress(cost_reg, depth_values, clamp_index):
+    """softmax + depth_regression + photometric confidence on [B,1,D,h,w] or [B,D,h,w] logits."""
+    logits = cost_reg.squeeze(1) if cost_reg.dim() == 5 else cost_reg
+    depth, conf, _, _ = ops.softargmin_conf(logits, depth_values, clamp_index=clamp_index)
+    return depth, conf
+
+
+def mvsnet_hot_path(features: List[torch.Tensor], proj_matrices, depth_values, cost_regularization):
+    """MVSNet.forward from 'step 2' to the returned dict (MVSNet/models/mvsnet.py:149-194, refine=False).
+    features: list of [B,32,h,w]; proj_matrices [B,N,4,4]; depth_values [B,D]."""
+    projs = torch.unbind(proj_matrices, 1)
+    assert len(features) == len(projs), "Different number of images and projection matrices"
+    var = build_cost_volume(features[0], features[1:], projs[0], projs[1:], depth_values)
+    depth, conf = regress(cost_regularization(var), depth_values, clamp_index=False)
+    return {"depth": depth, "photometric_confidence": conf}
+
+
+class DepthNet(nn.Module):
+    """Drop-in for CasMVSNet/models/cas_mvsnet.py:8-66: one cascade stage
+    (builder + CostRegNet + softmax/regression/confidence).  proj_matrices [B,N,2,4,4]."""
+
+    def forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization, prob_volume_init=None):
+        proj_matrices = torch.unbind(proj_matrices, 1)
+        assert len(features) == len(proj_matrices), "Different number of images and projection matrices"
+        assert depth_values.shape[1] == num_depth, f"depth_values.shape[1]:{depth_values.shape[1]}  num_depth:{num_depth}"
+        fused = []
+        for p in proj_matrices:      # K[:3,:3] @ E[:3,:4] per view (cas_mvsnet.py:30-33)
+            with torch.no_grad():
+                q = p[:, 0].clone()
+                q[:, :3, :4] = torch.matmul(p[:, 1, :3, :3], p[:, 0, :3, :4])
+            fused.append(q)
+        var = build_cost_volume(features[0], features[1:], fused[0], fused[1:], depth_values)
+        cost_reg = cost_regularization(var)
+        logits = cost_reg.squeeze(1)
+        if prob_volume_init is not None:
+            logits = logits + prob_volume_init
+        depth, conf = regress(logits, depth_values, clamp_index=True)
+        return {"depth": depth, "photometric_confidence": conf}
+
+
+def proj_cost(settings, ref_feature, src_feature, level, ref_in, src_in, ref_ex, src_ex, depth_hypos):
+    """Drop-in for CVP-MVSNet/models/modules.py:221-275 (per-pixel hypotheses; reproduces the
+    reference's aliasing quirk: the running sum starts from ref**2)."""
+    with torch.no_grad():
+        B = ref_in.shape[0]
+        last = torch.tensor([[[0, 0, 0, 1.0]]], device=ref_in.device, dtype=ref_in.dtype).repeat(B, 1, 1)
+        ref_proj = torch.cat((torch.matmul(ref_in, ref_ex[:, 0:3, :]), last), 1)
+        src_projs = [torch.cat((torch.matmul(src_in[:, s], src_ex[:, s, 0:3, :]), last), 1) for s in range(settings.nsrc)]
+    srcs = [src_feature[s][level] for s in range(settings.nsrc)]
+    return build_cost_volume(ref_feature, srcs, ref_proj, src_projs, depth_hypos, L.REF_SUM_SQUARED)

@@ -1,0 +1,361 @@
+"""Python face of the C-ABI: the reference's operator names and signatures over device tensors.
+
+Every function here validates its arguments, allocates the output with torch, and enqueues ONE
+call into libmvs_b200.so on torch's current CUDA stream.  There is no CPU path: tensors that are
+not on a CUDA device raise.  The tiny 4x4 projection algebra (inverse / matmul) stays in PyTorch
+exactly where the reference has it (MVSNet/models/module.py:63), so both sides of a parity test
+consume identical rot / trans bits.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from ._lib import lib, check
+
+__all__ = [
+    "relative_pose", "homo_warping", "homo_warping_cvp", "homo_warp", "warp_taps", "cost_volume",
+    "cost_volume_c8", "pack_c8", "unpack_c8", "conv3d", "softargmin_conf", "depth_regression",
+    "depth_regression_refine", "depth_range_samples",
+]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# Optional per-kernel CUDA-event timers (bench.py's roofline leg): events are recorded on the
+# launching stream around the named launches while KERNEL_TIMERS is a dict.
+KERNEL_TIMERS = None
+
+
+def _tic(name):
+    if KERNEL_TIMERS is None:
+        return None
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    KERNEL_TIMERS.setdefault(name, []).append((a, b))
+    a.record()
+    return b
+
+
+def _toc(ev):
+    if ev is not None:
+        ev.record()
+
+
+def _dev(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise L.MvsError("mvs_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on "
+                             f"{t.device}")
+    lib()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ptr_array(ts: Sequence[Optional[torch.Tensor]]):
+    arr = (C.c_void_p * len(ts))(*[0 if t is None else t.data_ptr() for t in ts])
+    return arr
+
+
+def _depth_mode(depth: torch.Tensor, B: int):
+    if depth.dim() == 2:
+        if depth.shape[0] != B:
+            raise ValueError(f"depth_values batch {depth.shape[0]} != {B}")
+        return L.DEPTH_PLANE
+    if depth.dim() == 4:
+        return L.DEPTH_PIXEL
+    raise ValueError(f"depth_values must be [B,D] or [B,D,H,W], got {tuple(depth.shape)}")
+
+
+def relative_pose(src_proj: torch.Tensor, ref_proj: torch.Tensor, ref_is_inverse: bool = False):
+    """proj = src_proj @ inverse(ref_proj) -> (rot [B,9], trans [B,3]) fp32 contiguous.
+    Same two torch ops as the reference (MVSNet/models/module.py:63-65)."""
+    with torch.no_grad():
+        proj = torch.matmul(src_proj, ref_proj if ref_is_inverse else torch.inverse(ref_proj))
+        rot = proj[:, :3, :3].reshape(-1, 9).float().contiguous()
+        trans = proj[:, :3, 3].float().contiguous()
+    return rot, trans
+
+
+def _warp(src_fea, rot, trans, depth_values, flags):
+    src_fea = _f32c(src_fea)
+    depth_values = _f32c(depth_values)
+    _dev(src_fea, rot, trans, depth_values)
+    B, Cc, H, W = src_fea.shape
+    D = depth_values.shape[1]
+    mode = _depth_mode(depth_values, B)
+    if mode == L.DEPTH_PIXEL and tuple(depth_values.shape) != (B, D, H, W):
+        raise ValueError(f"per-pixel depth_values must be [B,D,{H},{W}], got {tuple(depth_values.shape)}")
+    out = torch.empty((B, Cc, D, H, W), dtype=torch.float32, device=src_fea.device)
+    with torch.cuda.device(src_fea.device):
+        check(lib().mvs_warp_fwd(_p(src_fea), _p(rot), _p(trans), _p(depth_values), mode, _p(out), B, Cc, D, H, W,
+                                 flags, _stream()), "mvs_warp_fwd")
+    return out
+
+
+def homo_warping(src_fea, src_proj, ref_proj, depth_values):
+    """Drop-in for MVSNet/models/module.py:46 and CasMVSNet/models/module.py:245
+    (depth_values [B,D] or [B,D,H,W]) -> [B,C,D,H,W]."""
+    rot, trans = relative_pose(src_proj, ref_proj)
+    return _WarpFn.apply(src_fea, rot, trans, depth_values, 0)
+
+
+def homo_warping_cvp(src_feature, ref_in, src_in, ref_ex, src_ex, depth_hypos):
+    """Drop-in for CVP-MVSNet/models/modules.py:81 (K and E given separately, composed as
+    K @ E[:3] with a [0,0,0,1] row, modules.py:90-94)."""
+    with torch.no_grad():
+        last = torch.tensor([[[0, 0, 0, 1.0]]], device=src_in.device, dtype=src_in.dtype).repeat(len(src_in), 1, 1)
+        src_proj = torch.cat((torch.matmul(src_in, src_ex[:, 0:3, :]), last), 1)
+        ref_proj = torch.cat((torch.matmul(ref_in, ref_ex[:, 0:3, :]), last), 1)
+    return homo_warping(src_feature, src_proj, ref_proj, depth_hypos)
+
+
+def homo_warp(src_feat, src_proj, ref_proj_inv, depth_values):
+    """Drop-in for MVSNet_pl/models/modules.py:25 (pre-inverted ref matrix, align_corners=True,
+    R @ (xyz*d) + T op order)."""
+    rot, trans = relative_pose(src_proj, ref_proj_inv, ref_is_inverse=True)
+    return _WarpFn.apply(src_feat, rot, trans, depth_values, L.ALIGN_CORNERS | L.PL_ORDER)
+
+
+def warp_taps(rot, trans, depth_values, H, W, flags=0, want_ixy=True):
+    """Integer tap indices / in-bounds masks of the warp: x0, y0 int32, mask uint8 [B,D,H,W]."""
+    depth_values = _f32c(depth_values)
+    _dev(rot, trans, depth_values)
+    B, D = depth_values.shape[0], depth_values.shape[1]
+    mode = _depth_mode(depth_values, B)
+    dev = depth_values.device
+    x0 = torch.empty((B, D, H, W), dtype=torch.int32, device=dev)
+    y0 = torch.empty_like(x0)
+    mask = torch.empty((B, D, H, W), dtype=torch.uint8, device=dev)
+    ixy = torch.empty((B, D, H, W, 2), dtype=torch.float32, device=dev) if want_ixy else None
+    with torch.cuda.device(dev):
+        check(lib().mvs_warp_taps(_p(rot), _p(trans), _p(depth_values), mode, _p(x0), _p(y0), _p(mask), _p(ixy), B, D,
+                                  H, W, flags, _stream()), "mvs_warp_taps")
+    return x0, y0, mask, ixy
+
+
+def _stack_pose(rots, transs):
+    rot = torch.stack(rots, 1).contiguous()      # [B,nsrc,9]
+    trans = torch.stack(transs, 1).contiguous()  # [B,nsrc,3]
+    return rot, trans
+
+
+def _cost_volume_fwd(ref, srcs, rot, trans, depth_values, flags):
+    B, Cc, H, W = ref.shape
+    D = depth_values.shape[1]
+    mode = _depth_mode(depth_values, B)
+    nsrc = len(srcs)
+    if nsrc < 1:
+        raise ValueError("need at least one source view")
+    if nsrc > L.MAX_SRC:
+        raise ValueError(f"at most {L.MAX_SRC} source views per fused call, got {nsrc}")
+    for s in srcs:
+        if s.shape != ref.shape:
+            raise ValueError("source feature maps must have the reference map's shape")
+    out = torch.empty((B, Cc, D, H, W), dtype=torch.float32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        ev = _tic("warp_variance")
+        check(lib().mvs_warp_variance_fwd(_p(ref), _ptr_array(srcs), nsrc, _p(rot), _p(trans), _p(depth_values), mode,
+                                          _p(out), B, Cc, D, H, W, flags, _stream()), "mvs_warp_variance_fwd")
+        _toc(ev)
+    return out
+
+
+class _WarpFn(torch.autograd.Function):
+    """homo_warping with the reference's gradient structure: the sampling grid is built under
+    no_grad (module.py:62), so only src_fea receives a gradient."""
+
+    @staticmethod
+    def forward(ctx, src_fea, rot, trans, depth_values, flags):
+        depth_values = _f32c(depth_values)
+        ctx.save_for_backward(rot, trans, depth_values)
+        ctx.flags = flags
+        ctx.shape = tuple(src_fea.shape)
+        return _warp(src_fea, rot, trans, depth_values, flags)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rot, trans, depth_values = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        B, Cc, H, W = ctx.shape
+        D = depth_values.shape[1]
+        g_src = torch.zeros(ctx.shape, dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            check(lib().mvs_warp_bwd(_p(grad_out), _p(rot), _p(trans), _p(depth_values), _depth_mode(depth_values, B),
+                                     _p(g_src), B, Cc, D, H, W, ctx.flags, _stream()), "mvs_warp_bwd")
+        return g_src, None, None, None, None
+
+
+class _CostVolumeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, rot, trans, depth_values, flags, *srcs):
+        ref = _f32c(ref)
+        srcs = [_f32c(s) for s in srcs]
+        depth_values = _f32c(depth_values)
+        _dev(ref, rot, trans, depth_values, *srcs)
+        ctx.save_for_backward(ref, rot, trans, depth_values, *srcs)
+        ctx.flags = flags
+        return _cost_volume_fwd(ref, srcs, rot, trans, depth_values, flags)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ref, rot, trans, depth_values, *srcs = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        B, Cc, H, W = ref.shape
+        D = depth_values.shape[1]
+        g_ref = torch.zeros_like(ref)
+        g_srcs = [torch.zeros_like(s) for s in srcs]
+        with torch.cuda.device(ref.device):
+            check(lib().mvs_warp_variance_bwd(_p(grad_out), _p(ref), _ptr_array(srcs), len(srcs), _p(rot), _p(trans),
+                                              _p(depth_values), _depth_mode(depth_values, B), _p(g_ref),
+                                              _ptr_array(g_srcs), B, Cc, D, H, W, ctx.flags, _stream()),
+                  "mvs_warp_variance_bwd")
+        return (g_ref, None, None, None, None, *g_srcs)
+
+
+def cost_volume(ref_fea, src_feas, rots, transs, depth_values, flags=0):
+    """Fused builder, strict fp32: variance over (ref, warped srcs) -> [B,C,D,H,W] fp32.
+    rots/transs: per-source lists from relative_pose().  Differentiable w.r.t. the feature maps."""
+    rot, trans = _stack_pose(rots, transs)
+    return _CostVolumeFn.apply(ref_fea, rot, trans, depth_values, flags, *src_feas)
+
+
+def pack_c8(x: torch.Tensor) -> torch.Tensor:
+    """NC(D)HW fp32/bf16 -> C8 bf16 [B, ceil(C/8), *spatial, 8]."""
+    _dev(x)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    B, Cc = x.shape[:2]
+    spatial = tuple(x.shape[2:])
+    inner = 1
+    for s in spatial:
+        inner *= s
+    out = torch.empty((B, (Cc + 7) // 8, *spatial, 8), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().mvs_pack_c8(_p(x), L.F32 if x.dtype == torch.float32 else L.BF16, _p(out), B, Cc, inner,
+                                _stream()), "mvs_pack_c8")
+    return out
+
+
+def unpack_c8(x_c8: torch.Tensor, channels: int, dtype=torch.float32) -> torch.Tensor:
+    """C8 bf16 [B, CB, *spatial, 8] -> NC(D)HW `dtype`."""
+    _dev(x_c8)
+    assert x_c8.dtype == torch.bfloat16 and x_c8.shape[-1] == 8 and x_c8.is_contiguous()
+    B = x_c8.shape[0]
+    spatial = tuple(x_c8.shape[2:-1])
+    inner = 1
+    for s in spatial:
+        inner *= s
+    out = torch.empty((B, channels, *spatial), dtype=dtype, device=x_c8.device)
+    with torch.cuda.device(x_c8.device):
+        check(lib().mvs_unpack_c8(_p(x_c8), _p(out), L.F32 if dtype == torch.float32 else L.BF16, B, channels, inner,
+                                  _stream()), "mvs_unpack_c8")
+    return out
+
+
+def cost_volume_c8(ref_c8, srcs_c8, rots, transs, depth_values, flags=0):
+    """Fused builder, fast path: C8 bf16 feature maps [B,CB,H,W,8] -> C8 bf16 volume [B,CB,D,H,W,8]."""
+    depth_values = _f32c(depth_values)
+    rot, trans = _stack_pose(rots, transs)
+    _dev(ref_c8, rot, trans, depth_values, *srcs_c8)
+    B, CB, H, W, _ = ref_c8.shape
+    D = depth_values.shape[1]
+    mode = _depth_mode(depth_values, B)
+    nsrc = len(srcs_c8)
+    if not 1 <= nsrc <= L.MAX_SRC:
+        raise ValueError(f"1..{L.MAX_SRC} source views per fused call, got {nsrc}")
+    out = torch.empty((B, CB, D, H, W, 8), dtype=torch.bfloat16, device=ref_c8.device)
+    with torch.cuda.device(ref_c8.device):
+        ev = _tic("warp_variance")
+        check(lib().mvs_warp_variance_c8_fwd(_p(ref_c8), _ptr_array(srcs_c8), nsrc, _p(rot), _p(trans),
+                                             _p(depth_values), mode, _p(out), B, CB * 8, D, H, W, flags, _stream()),
+              "mvs_warp_variance_c8_fwd")
+        _toc(ev)
+    return out
+
+
+def conv3d(x, weight, scale=None, shift=None, skip=None, stride=1, transposed=False, relu=False):
+    """Strict fp32 NCDHW: y = [skip +] act(conv(x, w) * scale + shift); kernel 3, padding 1
+    (transposed: ConvTranspose3d(stride, padding=1, output_padding=stride-1))."""
+    x = _f32c(x)
+    weight = _f32c(weight)
+    _dev(x, weight, scale, shift, skip)
+    B, Cin, D, H, W = x.shape
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    if (weight.shape[0] if transposed else weight.shape[1]) != Cin or tuple(weight.shape[2:]) != (3, 3, 3):
+        raise ValueError(f"weight {tuple(weight.shape)} does not match Cin={Cin} / 3x3x3")
+    if transposed:
+        oshape = (B, Cout, D * stride, H * stride, W * stride)
+    else:
+        oshape = (B, Cout, (D - 1) // stride + 1, (H - 1) // stride + 1, (W - 1) // stride + 1)
+    if skip is not None:
+        skip = _f32c(skip)
+        if tuple(skip.shape) != oshape:
+            raise ValueError(f"skip {tuple(skip.shape)} != output {oshape}")
+    y = torch.empty(oshape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().mvs_conv3d_fwd(_p(x), _p(weight), _p(scale), _p(shift), _p(skip), _p(y), B, Cin, Cout, D, H, W,
+                                   stride, int(transposed), L.RELU if relu else 0, _stream()), "mvs_conv3d_fwd")
+    return y
+
+
+def softargmin_conf(logits, depth_values, clamp_index=False, want_prob=False, want_index=False, input_is_prob=False):
+    """Fused softmax over D + depth regression + photometric confidence.
+    logits [B,D,H,W] -> (depth [B,H,W], conf [B,H,W], prob|None, index|None)."""
+    logits = _f32c(logits)
+    depth_values = _f32c(depth_values)
+    _dev(logits, depth_values)
+    B, D, H, W = logits.shape
+    if depth_values.dim() == 1:
+        depth_values = depth_values.unsqueeze(0).expand(B, D).contiguous()
+    mode = _depth_mode(depth_values, B)
+    if depth_values.shape[1] != D:
+        raise ValueError(f"depth_values has {depth_values.shape[1]} hypotheses, logits have {D}")
+    dev = logits.device
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    conf = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    prob = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if want_prob else None
+    index = torch.empty((B, H, W), dtype=torch.int32, device=dev) if want_index else None
+    flags = (L.CLAMP_INDEX if clamp_index else 0) | (L.INPUT_IS_PROB if input_is_prob else 0)
+    with torch.cuda.device(dev):
+        check(lib().mvs_softargmin_conf_fwd(_p(logits), _p(depth_values), mode, _p(depth), _p(conf), _p(prob),
+                                            _p(index), B, D, H, W, flags, _stream()), "mvs_softargmin_conf_fwd")
+    return depth, conf, prob, index
+
+
+def depth_regression(p, depth_values):
+    """Drop-in for depth_regression(p, depth_values): MVSNet/models/module.py:91,
+    CasMVSNet/models/module.py:455 ([B,D] or [B,D,H,W]), CVP-MVSNet/models/modules.py:338.
+    `p` is a probability volume (already soft-maxed), as in the reference."""
+    return softargmin_conf(p, depth_values, input_is_prob=True)[0]
+
+
+def depth_regression_refine(prob_volume, depth_hypothesis):
+    """Drop-in for CVP-MVSNet/models/modules.py:352."""
+    return softargmin_conf(prob_volume, depth_hypothesis, input_is_prob=True)[0]
+
+
+def depth_range_samples(cur_depth, ndepth: int, depth_interval_pixel: float):
+    """Per-pixel branch of get_depth_range_samples (CasMVSNet/models/module.py:485-504):
+    cur_depth [B,H,W] -> [B,ndepth,H,W]."""
+    cur_depth = _f32c(cur_depth)
+    _dev(cur_depth)
+    B, H, W = cur_depth.shape
+    out = torch.empty((B, ndepth, H, W), dtype=torch.float32, device=cur_depth.device)
+    with torch.cuda.device(cur_depth.device):
+        check(lib().mvs_depth_range_samples(_p(cur_depth), float(depth_interval_pixel), ndepth, _p(out), B, H, W,
+                                            _stream()), "mvs_depth_range_samples")
+    return out

@@ -1,0 +1,64 @@
+"""patch_reference(): rebind the reference's hot-path names to the sm_100a implementations.
+
+The reference has no plugin registry; its model files do ``from .module import *``
+(MVSNet/models/mvsnet.py:4, CasMVSNet/models/cas_mvsnet.py:4, CVP-MVSNet/models/net.py:12), so the
+names must be replaced in the CONSUMER module's globals as well as in the defining module.
+train.py / eval.py / test.py then run unchanged.
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+from . import modules, ops
+
+_COMMON = {
+    "depth_regression": ops.depth_regression,
+}
+
+_BY_FAMILY = {
+    # MVSNet/models/{module,mvsnet}.py
+    "mvsnet": {"homo_warping": ops.homo_warping, "CostRegNet": modules.CostRegNetMVSNet,
+               "ConvBnReLU3D": modules.ConvBnReLU3D},
+    # CasMVSNet/models/{module,cas_mvsnet}.py
+    "cas": {"homo_warping": ops.homo_warping, "CostRegNet": modules.CostRegNetCas, "DepthNet": modules.DepthNet,
+            "Conv3d": modules.Conv3d, "Deconv3d": modules.Deconv3d},
+    # CVP-MVSNet/models/{modules,net}.py
+    "cvp": {"homo_warping": ops.homo_warping_cvp, "proj_cost": modules.proj_cost,
+            "depth_regression_refine": ops.depth_regression_refine, "CostRegNet": modules.CostRegNetCVP},
+    # MVSNet_pl/models/{modules,mvsnet}.py
+    "pl": {"homo_warp": ops.homo_warp},
+}
+
+
+def _family_of(mod: types.ModuleType) -> str:
+    names = set(vars(mod))
+    if "proj_cost" in names or "depth_regression_refine" in names or "network" in names:
+        return "cvp"
+    if "homo_warp" in names:
+        return "pl"
+    if "DepthNet" in names or "CascadeMVSNet" in names or "get_depth_range_samples" in names:
+        return "cas"
+    return "mvsnet"
+
+
+def patch_reference(*mods, family: str | None = None) -> dict:
+    """Rebind hot-path names inside already-imported reference modules.
+
+    ``patch_reference()`` with no arguments patches every loaded module named ``models.*``.
+    Returns {module_name: [patched names]}.
+    """
+    if not mods:
+        mods = tuple(m for n, m in list(sys.modules.items()) if m is not None and (n == "models" or n.startswith("models.")))
+    done = {}
+    for m in mods:
+        fam = family or _family_of(m)
+        table = dict(_COMMON)
+        table.update(_BY_FAMILY[fam])
+        hit = []
+        for name, repl in table.items():
+            if name in vars(m):
+                setattr(m, name, repl)
+                hit.append(name)
+        done[m.__name__] = hit
+    return done

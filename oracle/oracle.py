@@ -36,8 +36,11 @@ def build(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        try:
+            build()          # no-op when the .so is newer than the source
+        except Exception:
+            if not os.path.exists(_SO):
+                raise
         _lib = C.CDLL(_SO)
     return _lib
 
@@ -168,7 +171,7 @@ def depth_range_samples(cur, interval, ndepth):
     B, H, W = cur.shape
     out = np.empty((B, ndepth, H, W), np.float32)
     fn = lib().mvso_depth_range_samples
-    fn.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
+    fn.argtypes = [C.POINTER(C.c_float), C.c_double, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
     fn(p, float(interval), ndepth, out.ctypes.data_as(C.POINTER(C.c_float)), B, H, W)
     return out
 

@@ -1,0 +1,159 @@
+"""PyTorch-CPU restatement of the reference hot path, op for op (TEST / BASELINE INFRASTRUCTURE).
+
+Why this exists next to mvs_oracle.c: the reference's arithmetic engine IS PyTorch (ATen grid_sample,
+oneDNN conv3d, MKL matmul).  /root/reference cannot travel to the GPU box, so bench.py's
+`cpu_baseline` leg and `--impl reference` arm time THIS port on the box's host cores -- the same
+ATen kernels, with all host threads, that the reference's own modules would run there
+(`cpu_baseline.kind = "port"`).  tests/test_torch_port.py checks it against the golden fixtures
+generated from the unmodified reference (bit-exact for the warp / variance, since the op sequence
+is identical).
+
+Only tests/, bench.py (cpu_baseline / --impl reference) and __graft_entry__.smoke() import this.
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+import torch.nn.functional as F
+
+
+def warp_volume(src_fea, src_proj, ref_proj, depth_values, align_corners=None):
+    """MVSNet/models/module.py:46-87 and CasMVSNet/models/module.py:245-280 (depth [B,D] | [B,D,H,W])."""
+    B, C, H, W = src_fea.shape
+    D = depth_values.shape[1]
+    with torch.no_grad():
+        proj = src_proj @ torch.inverse(ref_proj)
+        rot, trans = proj[:, :3, :3], proj[:, :3, 3:4]
+        ys, xs = torch.meshgrid(torch.arange(0, H, dtype=torch.float32), torch.arange(0, W, dtype=torch.float32),
+                                indexing="ij")
+        pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(H * W)))          # [3, H*W]
+        rot_xyz = torch.matmul(rot, pix.unsqueeze(0).repeat(B, 1, 1))                   # [B, 3, H*W]
+        pts = rot_xyz.unsqueeze(2).repeat(1, 1, D, 1) * depth_values.view(B, 1, D, -1)  # [B, 3, D, H*W]
+        pts = pts + trans.view(B, 3, 1, 1)
+        uv = pts[:, :2] / pts[:, 2:3]
+        gx = uv[:, 0] / ((W - 1) / 2) - 1
+        gy = uv[:, 1] / ((H - 1) / 2) - 1
+        grid = torch.stack((gx, gy), dim=3)                                             # [B, D, H*W, 2]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if align_corners is None:
+            out = F.grid_sample(src_fea, grid.view(B, D * H, W, 2), mode="bilinear", padding_mode="zeros")
+        else:
+            out = F.grid_sample(src_fea, grid.view(B, D * H, W, 2), mode="bilinear", padding_mode="zeros",
+                                align_corners=align_corners)
+    return out.view(B, C, D, H, W)
+
+
+def variance_volume(ref_fea, src_feas, ref_proj, src_projs, depth_values, ref_sum_squared=False):
+    """Builder loop, eval branch: MVSNet/models/mvsnet.py:152-170 (in-place accumulation)."""
+    D = depth_values.shape[1]
+    n = len(src_feas) + 1
+    ref_volume = ref_fea.unsqueeze(2).repeat(1, 1, D, 1, 1)
+    if ref_sum_squared:   # CVP aliasing: net.py:129-130
+        vol_sq = ref_volume.pow_(2)
+        vol_sum = ref_volume
+        for fea, prj in zip(src_feas, src_projs):
+            w = warp_volume(fea, prj, ref_proj, depth_values)
+            vol_sum = vol_sum + w
+            vol_sq = vol_sq + w ** 2
+    else:
+        vol_sum = ref_volume
+        vol_sq = ref_volume ** 2
+        for fea, prj in zip(src_feas, src_projs):
+            w = warp_volume(fea, prj, ref_proj, depth_values)
+            vol_sum += w
+            vol_sq += w.pow_(2)
+    return vol_sq.div_(n).sub_(vol_sum.div_(n).pow_(2))
+
+
+def _cbr(x, sd, conv, bn, stride=1, transposed=False, eps=1e-5):
+    w = sd[conv + ".weight"]
+    if transposed:
+        y = F.conv_transpose3d(x, w, None, stride=stride, padding=1, output_padding=stride - 1)
+    else:
+        y = F.conv3d(x, w, None, stride=stride, padding=1)
+    y = F.batch_norm(y, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"], sd[bn + ".bias"],
+                     False, 0.1, eps)
+    return F.relu(y, inplace=True)
+
+
+def costreg(x, sd, family):
+    """CostRegNet.forward: MVSNet/models/mvsnet.py:84-93 | CasMVSNet/models/module.py:429-438 |
+    CVP-MVSNet/models/net.py:78-89, driven by a reference-keyed state dict of tensors."""
+    if family == "cvp":
+        c0 = _cbr(_cbr(x, sd, "conv0.conv", "conv0.bn"), sd, "conv0a.conv", "conv0a.bn")
+        c2 = _cbr(_cbr(_cbr(c0, sd, "conv1.conv", "conv1.bn", 2), sd, "conv2.conv", "conv2.bn"), sd, "conv2a.conv", "conv2a.bn")
+        c4 = _cbr(_cbr(_cbr(c2, sd, "conv3.conv", "conv3.bn"), sd, "conv4.conv", "conv4.bn"), sd, "conv4a.conv", "conv4a.bn")
+        c5 = c2 + _cbr(c4, sd, "conv5.0", "conv5.1", 1, True)
+        c6 = c0 + _cbr(c5, sd, "conv6.0", "conv6.1", 2, True)
+        return F.conv3d(c6, sd["prob0.weight"], sd.get("prob0.bias"), padding=1).squeeze(1)
+    dk = (lambda n: (n + ".0", n + ".1")) if family == "mvsnet" else (lambda n: (n + ".conv", n + ".bn"))
+    c0 = _cbr(x, sd, "conv0.conv", "conv0.bn")
+    c2 = _cbr(_cbr(c0, sd, "conv1.conv", "conv1.bn", 2), sd, "conv2.conv", "conv2.bn")
+    c4 = _cbr(_cbr(c2, sd, "conv3.conv", "conv3.bn", 2), sd, "conv4.conv", "conv4.bn")
+    y = _cbr(_cbr(c4, sd, "conv5.conv", "conv5.bn", 2), sd, "conv6.conv", "conv6.bn")
+    y = c4 + _cbr(y, sd, *dk("conv7"), 2, True)
+    y = c2 + _cbr(y, sd, *dk("conv9"), 2, True)
+    y = c0 + _cbr(y, sd, *dk("conv11"), 2, True)
+    return F.conv3d(y, sd["prob.weight"], sd.get("prob.bias"), padding=1)
+
+
+def regress(cost_reg, depth_values, clamp_index):
+    """softmax + depth_regression + photometric confidence: mvsnet.py:183-191 / cas_mvsnet.py:51-64."""
+    logits = cost_reg.squeeze(1) if cost_reg.dim() == 5 else cost_reg
+    p = F.softmax(logits, dim=1)
+    dv = depth_values.view(*depth_values.shape, 1, 1) if depth_values.dim() <= 2 else depth_values
+    depth = torch.sum(p * dv, 1)
+    D = p.shape[1]
+    with torch.no_grad():
+        sum4 = 4 * F.avg_pool3d(F.pad(p.unsqueeze(1), pad=(0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
+        idx = torch.sum(p * torch.arange(D, dtype=torch.float).view(1, D, 1, 1), 1).long()
+        if clamp_index:
+            idx = idx.clamp(min=0, max=D - 1)
+        conf = torch.gather(sum4, 1, idx.unsqueeze(1)).squeeze(1)
+    return depth, conf
+
+
+def cas_fuse_proj(p):
+    """K[:3,:3] @ E[:3,:4] composition per view, CasMVSNet/models/cas_mvsnet.py:30-33. p [B,2,4,4]."""
+    q = p[:, 0].clone()
+    q[:, :3, :4] = torch.matmul(p[:, 1, :3, :3], p[:, 0, :3, :4])
+    return q
+
+
+def cas_stage(feats, proj_matrices, depth_values, sd):
+    """DepthNet.forward (cas_mvsnet.py:12-66). feats: list of [B,C,h,w]; proj_matrices [B,N,2,4,4]."""
+    projs = [cas_fuse_proj(p) for p in torch.unbind(proj_matrices, 1)]
+    var = variance_volume(feats[0], feats[1:], projs[0], projs[1:], depth_values)
+    return regress(costreg(var, sd, "cas"), depth_values, clamp_index=True)
+
+
+def cas_cascade(features, proj_matrices, depth_values, sds, ndepths=(48, 32, 8), ratios=(4, 2, 1), img_hw=None):
+    """CascadeMVSNet.forward after feature extraction (cas_mvsnet.py:109-165)."""
+    H, W = img_hw
+    B = depth_values.shape[0]
+    depth_min = float(depth_values[0, 0]); depth_max = float(depth_values[0, -1])
+    depth_interval = (depth_max - depth_min) / depth_values.size(1)
+    out, depth = {}, None
+    for i, nd in enumerate(ndepths):
+        key = f"stage{i + 1}"
+        scale = (4, 2, 1)[i]
+        if depth is None:
+            lo, hi = depth_values[:, 0], depth_values[:, -1]
+            step = (hi - lo) / (nd - 1)
+            samples = lo.unsqueeze(1) + torch.arange(0, nd, dtype=lo.dtype).reshape(1, -1) * step.unsqueeze(1)
+            samples = samples.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, H, W)
+        else:
+            cur = F.interpolate(depth.detach().unsqueeze(1), [H, W], mode="bilinear", align_corners=False).squeeze(1)
+            half = nd / 2 * (ratios[i] * depth_interval)
+            lo, hi = cur - half, cur + half
+            step = (hi - lo) / (nd - 1)
+            samples = lo.unsqueeze(1) + torch.arange(0, nd, dtype=cur.dtype).reshape(1, -1, 1, 1) * step.unsqueeze(1)
+        hyp = F.interpolate(samples.unsqueeze(1), [nd, H // scale, W // scale], mode="trilinear",
+                            align_corners=False).squeeze(1)
+        d, c = cas_stage([f[key] for f in features], proj_matrices[key], hyp, sds[i])
+        depth = d
+        out[key] = {"depth": d, "photometric_confidence": c}
+    out.update(out[f"stage{len(ndepths)}"])
+    return out
