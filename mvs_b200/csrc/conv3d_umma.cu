@@ -1,24 +1,541 @@
-// bf16 C8 3x3x3 convolution on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulator,
-// TMA-staged bricks).  UNDER CONSTRUCTION in this revision: the entry points exist so that the ABI
-// is complete and callers fail loudly (MVS_ERR_UNSUPPORTED) instead of silently taking another path.
+// bf16 3x3x3 convolution on the 5th-generation tensor cores: tcgen05.mma (UMMA) implicit GEMM with
+// the accumulators in TMEM, operands read straight from shared memory in the C8 layout.
+// Replaces the cuDNN conv3d / conv_transpose3d + BatchNorm3d + ReLU + skip-add launches of
+// CostRegNet (MVSNet/models/mvsnet.py:55-93, CasMVSNet/models/module.py:115-200,407-438,
+// CVP-MVSNet/models/net.py:52-89).
+//
+// Why C8 makes this an implicit GEMM without im2col: in [B][C/8][D][H][W][8] bf16, eight consecutive
+// w-voxels x eight channels are 128 contiguous bytes -- exactly one UMMA "core matrix" of the
+// K-major, no-swizzle canonical layout ((8,n),2):((16B,SBO),LBO).  So for a tile of 128 consecutive
+// w-voxels (the MMA M dimension) staged once in shared memory with its halo, the A operand of tap
+// (kd,kh,kw) is the SAME bytes at a different start address: start = row(kd,kh) + kw*16 B, SBO = 128 B,
+// LBO = distance to the next 8-channel block.  The 27 taps x Cin/16 k-steps accumulate into one TMEM
+// tile [128 x N] (N = Cout padded to 16).  Cin = 8 layers pair two taps per K=16 step (LBO = 16 B);
+// stride-2 layers stage even / odd columns separately; transposed convs run as 8 output-parity
+// classes over input-resolution rows.  All of that is expressed as a per-layer table of MMA ops
+// built on the host (ConvPlan), so there is one kernel.
+//
+// CTA = 128 threads = one M tile; it owns (batch, h-block, w-block, Cout-tile) and walks the depth
+// axis with a ring of staged input depth-slabs, so every input byte is fetched (1 + 2/ht) times from
+// L2 and the packed weights are staged once per CTA.  Per depth step: stage new slab(s) -> fence ->
+// one thread issues the MMA table -> tcgen05.commit -> mbarrier -> all warps drain TMEM
+// (tcgen05.ld 32x32b), apply folded-BN affine + ReLU + skip, store C8 bf16 (or fp32 logits for the
+// Cout=1 `prob` layer).  Several CTAs per SM overlap each other's phases.
+#include <vector>
+
 #include "common.cuh"
+
+namespace mvs {
+
+constexpr int UM_THREADS = 128;
+constexpr int UM_COLS = 132;        // staged columns per row (128 + halo + pairing pad)
+constexpr int UM_MAX_OPS = 224;
+constexpr int UM_MAX_ACC = 16;
+constexpr int UM_MAX_KSTEPS = 112;
+
+enum UmMode { UM_CONV_S1 = 0, UM_CONV_S2 = 1, UM_DECONV_S2 = 2 };
+
+struct MmaOp {                // offsets in 16-byte units
+    uint16_t a_off;           // within a depth slab
+    uint16_t b_off;           // within the packed weights of this Cout tile
+    uint8_t a_lbo;            // A leading-byte-offset (distance between the two 8-channel K chunks)
+    uint8_t rd;               // which depth slab of the step (0..2)
+    uint8_t acc;              // accumulator index
+    uint8_t first;            // 1: overwrite the accumulator (first k-step of this step)
+};
+
+struct AccOut {               // where accumulator `acc` lands: od = od_mul*step + dd, oh = oh_mul*(h0+th) + dh
+    int8_t th, dd, dh, wadd;  // ow = w_mul*m + wadd
+};
+
+struct KStepSrc {             // weight source of the two K chunks of a k-step: tap index (-1: zeros), cin chunk
+    int8_t tap[2];
+    int8_t chunk[2];
+};
+
+struct ConvPlan {
+    int B, D, H, W, Do, Ho, Wo;
+    int cin_chunks, cout, cout_chunks, n, cout_tiles;
+    int mode, ht, rh, arr, rd, ring;
+    int slab_units, weight_units, tmem_cols;
+    int h_mul, h_base;        // h_in(r) = h_mul * h0 + h_base + r          (h0 = ht * blockIdx.y)
+    int d_mul, d_base;        // d_in(step, k) = d_mul * step + d_base + k
+    int w_step, w_base[2];    // w_in(arr, col) = w_step * (m0 + col) + w_base[arr]
+    int od_mul, oh_mul, w_mul;
+    int n_ops, n_acc, steps;
+    int relu, out_f32, has_skip;
+    MmaOp ops[UM_MAX_OPS];
+    AccOut acc[UM_MAX_ACC];
+};
+
+struct PackPlan {
+    int cin, cout, n, cout_tiles, n_ksteps, transposed_weights, flip;
+    KStepSrc ks[UM_MAX_KSTEPS];
+};
+
+// ---- device helpers (inline PTX; sm_100a) -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_units, uint32_t sbo_units)
+{
+    // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48)
+    // | base_offset[49,52)=0 | lbo_mode[52]=0 | layout_type[61,64)=0 (SWIZZLE_NONE / interleave)
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(lbo_units & 0x3FFF) << 16;
+    d |= (uint64_t)(sbo_units & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n)
+{
+    // InstrDescriptor: c_format[4,6)=1 (F32) | a_format[7,10)=1 (BF16) | b_format[10,13)=1 | a_major[15]=0 (K)
+    // | b_major[16]=0 (K) | n_dim[17,23)=N>>3 | m_dim[24,29)=M>>4
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(taddr), "r"(cols) : "memory");
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UM_THREADS)
+conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__ x, const uint4 *__restrict__ wpk,
+                   const float *__restrict__ scale, const float *__restrict__ shift, const uint4 *__restrict__ skip,
+                   void *__restrict__ y)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint4 *sw = reinterpret_cast<uint4 *>(smem_raw);                 // packed weights of this Cout tile
+    uint4 *sa = sw + P.weight_units;                                 // ring of depth slabs
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sa + (size_t)P.ring * P.slab_units);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * 128;
+    const int h0 = blockIdx.y * P.ht;
+    const int b = blockIdx.z / P.cout_tiles, ct = blockIdx.z % P.cout_tiles;
+
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    // weights: staged once per CTA
+    {
+        const uint4 *src = wpk + (size_t)ct * P.weight_units;
+        for (int i = tid; i < P.weight_units; i += UM_THREADS) sw[i] = __ldg(src + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = *tmem_slot;
+    const uint32_t sw_addr = smem_u32(sw), sa_addr = smem_u32(sa);
+    const uint32_t idesc = umma_idesc_bf16(128, P.n);
+
+    const int lines = P.rh * P.cin_chunks * P.arr;                    // staged lines of UM_COLS vectors per slab
+    const size_t plane_in = (size_t)P.H * P.W;
+    int d_staged = -(1 << 30);                                       // highest input depth already in the ring
+    uint32_t parity = 0;
+
+    for (int step = 0; step < P.steps; ++step) {
+        // ---- stage the depth slabs this step needs and the ring does not hold yet ----
+        for (int k = 0; k < P.rd; ++k) {
+            const int d_in = P.d_mul * step + P.d_base + k;
+            if (d_in <= d_staged) continue;
+            uint4 *slab = sa + (size_t)((d_in + 3 * P.ring) % P.ring) * P.slab_units;
+            const bool d_ok = d_in >= 0 && d_in < P.D;
+            for (int ln = warp; ln < lines; ln += UM_THREADS / 32) {
+                const int a = ln % P.arr, chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
+                const int h_in = P.h_mul * h0 + P.h_base + r;
+                const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
+                const uint4 *src = x + (((size_t)b * P.cin_chunks + chunk) * P.D + (row_ok ? d_in : 0)) * plane_in +
+                                   (size_t)(row_ok ? h_in : 0) * P.W;
+                uint4 *dst = slab + (size_t)ln * UM_COLS;
+                for (int c = lane; c < UM_COLS; c += 32) {
+                    const int w_in = P.w_step * (m0 + c) + P.w_base[a];
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (row_ok && w_in >= 0 && w_in < P.W) v = __ldg(src + w_in);
+                    dst[c] = v;
+                }
+            }
+            d_staged = d_in;
+        }
+        fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+
+        // ---- one thread issues the whole MMA table of this step ----
+        if (tid == 0) {
+            tc_fence_after();
+            uint32_t slab_addr[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int d_in = P.d_mul * step + P.d_base + k;
+                slab_addr[k] = sa_addr + (uint32_t)(((d_in + 3 * P.ring) % P.ring) * P.slab_units) * 16u;
+            }
+            for (int i = 0; i < P.n_ops; ++i) {
+                const MmaOp op = P.ops[i];
+                const uint64_t ad = umma_smem_desc(slab_addr[op.rd] + (uint32_t)op.a_off * 16u, op.a_lbo, 8);
+                const uint64_t bd = umma_smem_desc(sw_addr + (uint32_t)op.b_off * 16u, (uint32_t)P.n, 8);
+                umma_bf16_ss(taddr + (uint32_t)op.acc * (uint32_t)P.n, ad, bd, idesc, op.first ? 0u : 1u);
+            }
+            umma_commit(mbar);
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        tc_fence_after();
+
+        // ---- epilogue: TMEM -> registers -> affine/ReLU/skip -> global ----
+        const int m = warp * 32 + lane;                               // row of the M tile owned by this thread
+        for (int a = 0; a < P.n_acc; ++a) {
+            const AccOut ao = P.acc[a];
+            const int od = P.od_mul * step + ao.dd;
+            const int oh = P.oh_mul * (h0 + ao.th) + ao.dh;
+            const int ow = P.w_mul * (m0 + m) + ao.wadd;
+            const bool ok = od < P.Do && oh < P.Ho && ow < P.Wo;      // warp-uniform except for ow
+            for (int n0 = 0; n0 < P.n; n0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * P.n + n0), v);
+                const int c0 = ct * P.n + n0;
+                if (!ok || c0 >= P.cout) continue;
+                if (P.out_f32) {
+                    float o = v[0] * (scale ? __ldg(scale) : 1.f) + (shift ? __ldg(shift) : 0.f);
+                    if (P.relu) o = fmaxf(o, 0.f);
+                    reinterpret_cast<float *>(y)[(((size_t)b * P.Do + od) * P.Ho + oh) * P.Wo + ow] = o;
+                    continue;
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int cc = c0 + half * 8;
+                    if (cc >= P.cout_chunks * 8) break;
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = cc + e;
+                        const float sc = (scale && c < P.cout) ? __ldg(scale + c) : 1.f;
+                        const float sh = (shift && c < P.cout) ? __ldg(shift + c) : 0.f;
+                        float t = fmaf(v[half * 8 + e], sc, sh);
+                        if (P.relu) t = fmaxf(t, 0.f);
+                        o[e] = c < P.cout ? t : 0.f;
+                    }
+                    const size_t oidx = ((((size_t)b * P.cout_chunks + (cc >> 3)) * P.Do + od) * P.Ho + oh) * P.Wo + ow;
+                    if (P.has_skip) {
+                        const uint4 s = __ldg(skip + oidx);
+                        const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            o[2 * e] += __uint_as_float(sv[e] << 16);
+                            o[2 * e + 1] += __uint_as_float(sv[e] & 0xffff0000u);
+                        }
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+                    pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+                    reinterpret_cast<uint4 *>(y)[oidx] = pk;
+                }
+            }
+        }
+        tc_fence_before();             // TMEM reads done before the next step's MMAs overwrite the accumulators
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(taddr, (uint32_t)P.tmem_cols);
+}
+
+// Packs fp32 weights into the per-k-step B blocks: [cout_tile][kstep][2 chunks][N rows][8] bf16.
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, __nv_bfloat16 *__restrict__ out)
+{
+    const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * P.n * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i % 8);
+        const int row = (int)((i / 8) % P.n);
+        const int j = (int)((i / (8LL * P.n)) % 2);
+        const int ks = (int)((i / (16LL * P.n)) % P.n_ksteps);
+        const int ct = (int)(i / (16LL * P.n * P.n_ksteps));
+        const int tap = P.ks[ks].tap[j];
+        const int ci = P.ks[ks].chunk[j] * 8 + e, co = ct * P.n + row;
+        float v = 0.f;
+        if (tap >= 0 && ci < P.cin && co < P.cout) {
+            const int t = P.flip ? 26 - tap : tap;
+            v = P.transposed_weights ? w[((size_t)ci * P.cout + co) * 27 + t] : w[((size_t)co * P.cin + ci) * 27 + t];
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- host: layer plan ------------------------------------------------------------------------------
+struct KStep {
+    int rd, rh, arr, col, chunk, lbo;    // A operand: depth slab, row offset (relative to S*th), array, column shift, chunk
+    int cls;                             // deconv output parity class (pd*4 + ph*2 + pw), 0 otherwise
+    KStepSrc src;
+};
+
+struct LayerGeom {
+    int mode, cin_chunks, n, cout_tiles, arr;
+    std::vector<KStep> ks;
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
+{
+    LayerGeom g;
+    g.mode = transposed ? (stride == 2 ? UM_DECONV_S2 : UM_CONV_S1) : (stride == 2 ? UM_CONV_S2 : UM_CONV_S1);
+    g.cin_chunks = (Cin + 7) / 8;
+    const int n_full = round_up(Cout, 16);
+    g.n = n_full > 32 ? 32 : n_full;                // Cout tiles of <= 32 keep the packed weights within smem
+    g.cout_tiles = (n_full + g.n - 1) / g.n;
+    g.arr = g.mode == UM_CONV_S2 ? 2 : 1;
+    const int CH = g.cin_chunks;
+    const int plane = g.arr * UM_COLS;               // 16 B units between consecutive chunks of one staged row
+    auto add = [&](int rd, int rh, int arr, int col, int chunk, int lbo, int cls, int tap0, int ch0, int tap1, int ch1) {
+        KStep k{rd, rh, arr, col, chunk, lbo, cls, {{(int8_t)tap0, (int8_t)tap1}, {(int8_t)ch0, (int8_t)ch1}}};
+        g.ks.push_back(k);
+    };
+    if (g.mode == UM_CONV_S1 || g.mode == UM_CONV_S2) {
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh) {
+                auto tap = [&](int kw) { return (kd * 3 + kh) * 3 + kw; };
+                // (array, column shift) of tap kw: stride 1: in[ow-1+kw]; stride 2: kw=0 -> O[c], 1 -> E[c], 2 -> O[c+1]
+                const int arr_of[3] = {g.mode == UM_CONV_S2 ? 1 : 0, 0, g.mode == UM_CONV_S2 ? 1 : 0};
+                const int col_of[3] = {0, g.mode == UM_CONV_S2 ? 0 : 1, g.mode == UM_CONV_S2 ? 1 : 2};
+                if (CH == 1) {
+                    // Cin = 8: K=16 pairs two taps whose staged columns are adjacent (LBO = 16 B)
+                    if (g.mode == UM_CONV_S1) {
+                        add(kd, kh, 0, 0, 0, 1, 0, tap(0), 0, tap(1), 0);
+                        add(kd, kh, 0, 2, 0, 1, 0, tap(2), 0, -1, 0);
+                    } else {
+                        add(kd, kh, 1, 0, 0, 1, 0, tap(0), 0, tap(2), 0);      // O[c], O[c+1]
+                        add(kd, kh, 0, 0, 0, 1, 0, tap(1), 0, -1, 0);          // E[c], (E[c+1] x 0)
+                    }
+                } else {
+                    for (int kw = 0; kw < 3; ++kw)
+                        for (int s = 0; s < CH; s += 2) {
+                            const bool pair = s + 1 < CH;
+                            add(kd, kh, arr_of[kw], col_of[kw], s, pair ? plane : 1, 0, tap(kw), s, pair ? tap(kw) : -1, s + 1);
+                        }
+                }
+            }
+    } else {
+        // transposed stride 2: o = 2i - 1 + k.  parity 0: k=1 (i = o/2); parity 1: k=0 (i+1), k=2 (i).
+        for (int pd = 0; pd < 2; ++pd)
+            for (int ph = 0; ph < 2; ++ph)
+                for (int pw = 0; pw < 2; ++pw)
+                    for (int kd = 0; kd < 3; ++kd) {
+                        if ((pd == 0) != (kd == 1)) continue;
+                        for (int kh = 0; kh < 3; ++kh) {
+                            if ((ph == 0) != (kh == 1)) continue;
+                            for (int kw = 0; kw < 3; ++kw) {
+                                if ((pw == 0) != (kw == 1)) continue;
+                                const int t = (kd * 3 + kh) * 3 + kw;
+                                for (int s = 0; s < CH; s += 2) {
+                                    const bool pair = s + 1 < CH;
+                                    add(kd == 0 ? 1 : 0, kh == 0 ? 1 : 0, 0, kw == 0 ? 1 : 0, s, pair ? plane : 1,
+                                        pd * 4 + ph * 2 + pw, t, s, pair ? t : -1, s + 1);
+                                }
+                            }
+                        }
+                    }
+    }
+    return g;
+}
+
+static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
+                       int transposed, int flags, bool out_f32, bool has_skip, size_t &smem_bytes)
+{
+    memset(&P, 0, sizeof(P));
+    P.B = B; P.D = D; P.H = H; P.W = W;
+    const bool deconv = g.mode == UM_DECONV_S2;
+    if (deconv) { P.Do = 2 * D; P.Ho = 2 * H; P.Wo = 2 * W; }
+    else if (g.mode == UM_CONV_S2) { P.Do = (D - 1) / 2 + 1; P.Ho = (H - 1) / 2 + 1; P.Wo = (W - 1) / 2 + 1; }
+    else { P.Do = D; P.Ho = H; P.Wo = W; }
+    P.cin_chunks = g.cin_chunks; P.cout = Cout; P.cout_chunks = (Cout + 7) / 8; P.n = g.n; P.cout_tiles = g.cout_tiles;
+    P.mode = g.mode; P.arr = g.arr;
+    P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip;
+    const int S = g.mode == UM_CONV_S2 ? 2 : 1;
+    const int per_row_ks = deconv ? 0 : (int)g.ks.size();
+    const int acc_per_row = deconv ? 8 : 1;
+    const int ops_per_row = deconv ? (int)g.ks.size() : per_row_ks;
+    P.weight_units = (int)g.ks.size() * 2 * g.n;
+    P.rd = deconv ? 2 : 3;
+    P.ring = P.rd;
+    const int rows_h = deconv ? H : P.Ho;
+    // choose ht: as many rows as the op table / TMEM / shared memory allow, preferring 2 CTAs per SM
+    int best = 0;
+    for (int pass = 0; pass < 2 && !best; ++pass) {
+        const size_t budget = pass == 0 ? 110 * 1024 : 225 * 1024;
+        for (int ht = 8; ht >= 1; --ht) {
+            if (ht > rows_h && ht > 1) continue;
+            if (ht * ops_per_row > UM_MAX_OPS || ht * acc_per_row > UM_MAX_ACC || ht * acc_per_row * g.n > 512) continue;
+            const int rh = deconv ? ht + 1 : S * (ht - 1) + 3;
+            const size_t bytes = ((size_t)P.weight_units + (size_t)P.ring * rh * g.cin_chunks * g.arr * UM_COLS) * 16 + 64;
+            if (bytes > budget) continue;
+            best = ht;
+            break;
+        }
+    }
+    if (!best) return false;
+    P.ht = best;
+    P.rh = deconv ? P.ht + 1 : S * (P.ht - 1) + 3;
+    P.slab_units = P.rh * g.cin_chunks * g.arr * UM_COLS;
+    smem_bytes = ((size_t)P.weight_units + (size_t)P.ring * P.slab_units) * 16 + 64;
+    P.n_acc = P.ht * acc_per_row;
+    int cols = 32;
+    while (cols < P.n_acc * g.n) cols *= 2;
+    P.tmem_cols = cols;
+    if (deconv) {
+        P.h_mul = 1; P.h_base = 0; P.d_mul = 1; P.d_base = 0; P.w_step = 1; P.w_base[0] = 0; P.w_base[1] = 0;
+        P.od_mul = 2; P.oh_mul = 2; P.w_mul = 2; P.steps = D;
+    } else {
+        P.h_mul = S; P.h_base = -1; P.d_mul = S; P.d_base = -1; P.w_step = S;
+        P.w_base[0] = S == 1 ? -1 : 0; P.w_base[1] = -1;
+        P.od_mul = 1; P.oh_mul = 1; P.w_mul = 1; P.steps = P.Do;
+    }
+    const int plane = g.arr * UM_COLS;
+    int n_ops = 0;
+    for (int th = 0; th < P.ht; ++th) {
+        bool seen[8] = {false, false, false, false, false, false, false, false};
+        for (size_t k = 0; k < g.ks.size(); ++k) {
+            const KStep &ks = g.ks[k];
+            MmaOp op;
+            const int row = S * th + ks.rh;
+            op.a_off = (uint16_t)(((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col);
+            op.b_off = (uint16_t)(k * 2 * g.n);
+            op.a_lbo = (uint8_t)ks.lbo;
+            op.rd = (uint8_t)ks.rd;
+            op.acc = (uint8_t)(th * acc_per_row + ks.cls);
+            op.first = seen[ks.cls] ? 0 : 1;
+            seen[ks.cls] = true;
+            if (ks.lbo > 255 || (int)op.a_off != ((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col) return false;
+            P.ops[n_ops++] = op;
+        }
+        for (int c = 0; c < acc_per_row; ++c) {
+            AccOut &ao = P.acc[th * acc_per_row + c];
+            ao.th = (int8_t)th;
+            ao.dd = deconv ? (int8_t)(c >> 2) : 0;
+            ao.dh = deconv ? (int8_t)((c >> 1) & 1) : 0;
+            ao.wadd = deconv ? (int8_t)(c & 1) : 0;
+        }
+    }
+    (void)plane;
+    P.n_ops = n_ops;
+    return true;
+}
+
+}  // namespace mvs
 
 using namespace mvs;
 
 extern "C" int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stride, int transposed)
 {
-    (void)stride; (void)transposed;
-    const int64_t cin8 = (Cin + 7) / 8 * 8, cout16 = (Cout + 15) / 16 * 16;
-    return cin8 * cout16 * 27 * 2;
+    if (Cin <= 0 || Cout <= 0 || (stride != 1 && stride != 2)) return -1;
+    const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
+    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * g.n * 16;
 }
 
-extern "C" int mvs_conv3d_c8_pack_weights(const float *, void *, int, int, int, int, void *)
+extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride, int transposed,
+                                          void *stream)
 {
-    return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_pack_weights: tcgen05 conv path not built in this revision");
+    MVS_REQUIRE(w && packed, "null pointer");
+    MVS_REQUIRE(Cin > 0 && Cout > 0 && (stride == 1 || stride == 2), "bad layer shape");
+    const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
+    MVS_REQUIRE((int)g.ks.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
+    PackPlan pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.cin = Cin; pp.cout = Cout; pp.n = g.n; pp.cout_tiles = g.cout_tiles; pp.n_ksteps = (int)g.ks.size();
+    pp.transposed_weights = transposed ? 1 : 0;
+    pp.flip = (transposed && stride == 1) ? 1 : 0;       // ConvTranspose3d(stride 1, pad 1) == conv with flipped taps
+    for (size_t k = 0; k < g.ks.size(); ++k) pp.ks[k] = g.ks[k].src;
+    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * g.n * 8;
+    pack_weights_kernel<<<cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        pp, w, (__nv_bfloat16 *)packed);
+    return check_launch("mvs_conv3d_c8_pack_weights");
 }
 
-extern "C" int mvs_conv3d_c8_fwd(const void *, const void *, const float *, const float *, const void *, void *, int, int,
-                                 int, int, int, int, int, int, int, void *)
+extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const float *scale, const float *shift,
+                                 const void *skip_c8, void *y, int B, int Cin, int Cout, int D, int H, int W, int stride,
+                                 int transposed, int flags, void *stream)
 {
-    return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_fwd: tcgen05 conv path not built in this revision");
+    if (B == 0 || D == 0 || H == 0 || W == 0) return MVS_OK;
+    MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "extents must be positive");
+    MVS_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
+    MVS_REQUIRE(x_c8 && w_packed && y, "null pointer");
+    const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
+    MVS_REQUIRE((int)g.ks.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
+    static thread_local ConvPlan P;
+    size_t smem = 0;
+    const bool out_f32 = Cout == 1;
+    if (!build_plan(P, g, B, Cin, Cout, D, H, W, stride, transposed, flags, out_f32, skip_c8 != nullptr, smem))
+        return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_fwd: no tile configuration fits shared memory / TMEM for this layer");
+    MVS_REQUIRE(!(out_f32 && skip_c8), "skip is not supported on the fp32 (Cout == 1) output");
+    const int rows_h = g.mode == UM_DECONV_S2 ? H : P.Ho;
+    const int m_ext = g.mode == UM_DECONV_S2 ? W : P.Wo;
+    dim3 grid(cdiv(m_ext, 128), cdiv(rows_h, P.ht), B * P.cout_tiles);
+    MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "grid too large");
+    cudaError_t e = cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    conv3d_umma_kernel<<<grid, UM_THREADS, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed,
+                                                                         scale, shift, (const uint4 *)skip_c8, y);
+    return check_launch("mvs_conv3d_c8_fwd");
 }

@@ -101,7 +101,22 @@ def _run_layer(x, weight, bn, stride, transposed, relu, skip, mode, owner):
     scale, shift = _fold_bn(bn, owner)
     if mode == "strict":
         return ops.conv3d(x, weight, scale, shift, skip, stride, transposed, relu)
-    raise L.MvsError(f"CostRegNet mode {mode!r}: only 'strict' is wired up in this revision")
+    if mode == "fast":
+        cin = weight.shape[0] if transposed else weight.shape[1]
+        cout = weight.shape[1] if transposed else weight.shape[0]
+        return ops.conv3d_c8(x, _packed(weight, stride, transposed, owner), cin, cout, scale, shift, skip, stride,
+                             transposed, relu)
+    raise L.MvsError(f"unknown CostRegNet mode {mode!r} (use 'strict' or 'fast')")
+
+
+def _packed(weight, stride, transposed, owner):
+    """tcgen05 weight blocks, re-packed only when the parameter is modified or replaced."""
+    key = (weight.data_ptr(), weight._version, stride, transposed)
+    cached = getattr(owner, "_mvs_packed", None)
+    if cached is None or cached[0] != key:
+        cached = (key, ops.pack_conv_weights(weight, stride, transposed))
+        owner._mvs_packed = cached
+    return cached[1]
 
 
 def _seq_layer(seq: nn.Sequential, x, skip, mode):
@@ -207,16 +222,20 @@ class CostRegNetCVP(nn.Module):
 
 
 def _check_divisible(x, k):
-    if any(s % k for s in x.shape[2:]):
+    dims = x.shape[2:5]           # D,H,W for both NCDHW and C8 ([B,CB,D,H,W,8]) tensors
+    if any(s % k for s in dims):
         raise ValueError(f"CostRegNet needs D,H,W divisible by {k} for its skip adds "
-                         f"(the reference fails at the add, mvsnet.py:89-91); got {tuple(x.shape[2:])}")
+                         f"(the reference fails at the add, mvsnet.py:89-91); got {tuple(dims)}")
 
 
 def _prob_layer(conv: nn.Conv3d, x, mode):
     shift = conv.bias.detach().float() if conv.bias is not None else None
     if mode == "strict":
         return ops.conv3d(x, conv.weight, None, shift, None, 1, False, False)
-    raise L.MvsError(f"CostRegNet mode {mode!r}: only 'strict' is wired up in this revision")
+    if mode == "fast":
+        return ops.conv3d_c8(x, _packed(conv.weight, 1, False, conv), conv.weight.shape[1], 1, None, shift, None, 1,
+                             False, False)
+    raise L.MvsError(f"unknown CostRegNet mode {mode!r} (use 'strict' or 'fast')")
 
 
 def CostRegNet(*args, **kwargs):

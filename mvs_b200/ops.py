@@ -359,3 +359,50 @@ def depth_range_samples(cur_depth, ndepth: int, depth_interval_pixel: float):
         check(lib().mvs_depth_range_samples(_p(cur_depth), float(depth_interval_pixel), ndepth, _p(out), B, H, W,
                                             _stream()), "mvs_depth_range_samples")
     return out
+
+
+# ---- fast path: bf16 C8 convolution on the tcgen05 tensor cores -----------------------------------
+def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = False) -> torch.Tensor:
+    """fp32 [Cout,Cin,3,3,3] (or [Cin,Cout,3,3,3] when transposed) -> opaque packed bf16 blocks for
+    conv3d_c8 (uint8 tensor on the weight's device)."""
+    weight = _f32c(weight.detach())
+    _dev(weight)
+    cin = weight.shape[0] if transposed else weight.shape[1]
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    nbytes = int(lib().mvs_conv3d_c8_packed_weight_bytes(cin, cout, stride, int(transposed)))
+    if nbytes <= 0:
+        raise ValueError(f"unsupported layer shape Cin={cin} Cout={cout} stride={stride}")
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        check(lib().mvs_conv3d_c8_pack_weights(_p(weight), _p(packed), cin, cout, stride, int(transposed), _stream()),
+              "mvs_conv3d_c8_pack_weights")
+    return packed
+
+
+def conv3d_c8(x_c8, packed_w, cin: int, cout: int, scale=None, shift=None, skip_c8=None, stride=1, transposed=False,
+              relu=False):
+    """y = [skip +] act(conv(x, w) * scale + shift) on C8 bf16 activations [B,CB,D,H,W,8].
+    Returns C8 bf16 [B,ceil(Cout/8),Do,Ho,Wo,8], or fp32 [B,1,Do,Ho,Wo] when Cout == 1 (`prob`)."""
+    _dev(x_c8, packed_w, scale, shift, skip_c8)
+    if x_c8.dtype != torch.bfloat16 or x_c8.dim() != 6 or x_c8.shape[-1] != 8 or not x_c8.is_contiguous():
+        raise ValueError("x_c8 must be a contiguous C8 bf16 tensor [B,CB,D,H,W,8]")
+    B, CB, D, H, W, _ = x_c8.shape
+    if CB != (cin + 7) // 8:
+        raise ValueError(f"x_c8 has {CB} channel blocks, Cin={cin} needs {(cin + 7) // 8}")
+    if transposed and stride == 2:
+        Do, Ho, Wo = 2 * D, 2 * H, 2 * W
+    elif stride == 2:
+        Do, Ho, Wo = (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    else:
+        Do, Ho, Wo = D, H, W
+    if cout == 1:
+        y = torch.empty((B, 1, Do, Ho, Wo), dtype=torch.float32, device=x_c8.device)
+    else:
+        y = torch.empty((B, (cout + 7) // 8, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=x_c8.device)
+    if skip_c8 is not None and (skip_c8.shape != y.shape or skip_c8.dtype != torch.bfloat16 or not skip_c8.is_contiguous()):
+        raise ValueError("skip_c8 must be a contiguous C8 bf16 tensor of the output's shape")
+    with torch.cuda.device(x_c8.device):
+        check(lib().mvs_conv3d_c8_fwd(_p(x_c8), _p(packed_w), _p(scale), _p(shift), _p(skip_c8), _p(y), B, cin, cout, D,
+                                      H, W, stride, int(transposed), L.RELU if relu else 0, _stream()),
+              "mvs_conv3d_c8_fwd")
+    return y

@@ -1,0 +1,92 @@
+"""GPU tests of the bf16 tcgen05 (UMMA) convolution path against the CPU oracle.
+The oracle is fed the SAME bf16-rounded activations and weights, so the only differences are fp32
+accumulation order and the single bf16 rounding of the stored output (rel 2^-8)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def bf(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).bfloat16().float().numpy()
+
+
+LAYERS = [
+    # cin, cout, stride, transposed, (D, H, W)
+    (8, 8, 1, False, (3, 5, 40)),        # conv0 stage 3: Cin=8 tap pairing
+    (16, 8, 1, False, (4, 9, 150)),      # conv0 stage 2, ragged W > 128
+    (32, 8, 1, False, (2, 4, 130)),      # conv0 stage 1
+    (8, 16, 2, False, (5, 7, 61)),       # conv1: stride 2, Cin=8, odd extents
+    (16, 16, 1, False, (4, 6, 50)),      # conv2
+    (16, 32, 2, False, (4, 6, 300)),     # conv3: stride 2, two M tiles after striding
+    (32, 32, 1, False, (3, 5, 37)),      # conv4
+    (32, 64, 2, False, (4, 8, 50)),      # conv5: two Cout tiles
+    (64, 64, 1, False, (2, 3, 25)),      # conv6
+    (64, 32, 2, True, (2, 3, 25)),       # conv7: transposed
+    (32, 16, 2, True, (2, 5, 70)),       # conv9 (2*70 = 140 outputs per row)
+    (16, 8, 2, True, (3, 4, 130)),       # conv11: two M tiles
+    (8, 1, 1, False, (4, 6, 133)),       # prob: fp32 logits out
+    (64, 32, 1, True, (2, 4, 20)),       # CVP conv5: transposed stride 1
+]
+
+
+@pytest.mark.parametrize("cin,cout,stride,transposed,dhw", LAYERS)
+def test_conv3d_c8_layer(cin, cout, stride, transposed, dhw):
+    from mvs_b200 import ops
+    rng = np.random.RandomState(cin * 1000 + cout * 10 + stride + 2 * transposed)
+    D, H, W = dhw
+    B = 2
+    x = bf(rng.standard_normal((B, cin, D, H, W)).astype(np.float32))
+    wshape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+    w = bf((rng.standard_normal(wshape) / np.sqrt(27 * cin)).astype(np.float32))
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = (0.3 * rng.standard_normal(cout)).astype(np.float32)
+    ref = O.conv3d(x, w, None, stride, transposed)
+    ref = ref * scale.reshape(1, -1, 1, 1, 1) + shift.reshape(1, -1, 1, 1, 1)
+    relu = cout != 1
+    if relu:
+        ref = np.maximum(ref, 0)
+    skip = None
+    if cout != 1:
+        skip = bf(rng.standard_normal(ref.shape).astype(np.float32))
+        ref = skip + ref
+    packed = ops.pack_conv_weights(cu(w), stride, transposed)
+    y = ops.conv3d_c8(ops.pack_c8(cu(x)), packed, cin, cout, cu(scale), cu(shift),
+                      ops.pack_c8(cu(skip)) if skip is not None else None, stride, transposed, relu)
+    torch.cuda.synchronize()
+    if cout == 1:
+        out = y.cpu().numpy()
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+    else:
+        out = ops.unpack_c8(y, cout).cpu().numpy()
+        assert out.shape == ref.shape
+        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=4e-3)
+
+
+@pytest.mark.parametrize("family,cin", [("mvsnet", 32), ("cas", 16), ("cas", 8), ("cvp", 16)])
+def test_costreg_fast_vs_strict(family, cin):
+    """Whole CostRegNet on the tensor-core path vs the strict fp32 path (same weights)."""
+    from mvs_b200 import modules, ops
+    sd = cases.costreg_state(family, cin=cin, seed=60)
+    def make(mode):
+        net = {"mvsnet": lambda: modules.CostRegNetMVSNet(mode=mode), "cas": lambda: modules.CostRegNetCas(cin, 8, mode=mode),
+               "cvp": lambda: modules.CostRegNetCVP(mode=mode)}[family]()
+        net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+        return net.to(DEV).eval()
+    x = torch.randn(1, cin, 8, 16, 136, device=DEV).bfloat16().float()
+    with torch.no_grad():
+        ref = make("strict")(x)
+        out = make("fast")(ops.pack_c8(x))
+    if family == "cvp":
+        assert out.shape == ref.shape
+    err = (out.float().reshape(ref.shape) - ref).abs().max().item()
+    assert err <= 0.03 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
