@@ -15,33 +15,38 @@
 // classes over input-resolution rows.  All of that is expressed as a per-layer table of MMA ops
 // built on the host (ConvPlan), so there is one kernel.
 //
-// CTA = 128 threads = one M tile; it owns (batch, h-block, w-block, Cout-tile) and walks the depth
-// axis with a ring of staged input depth-slabs, so every input byte is fetched (1 + 2/ht) times from
-// L2 and the packed weights are staged once per CTA.  Per depth step: stage new slab(s) -> fence ->
-// one thread issues the MMA table -> tcgen05.commit -> mbarrier -> all warps drain TMEM
-// (tcgen05.ld 32x32b), apply folded-BN affine + ReLU + skip, store C8 bf16 (or fp32 logits for the
-// Cout=1 `prob` layer).  Several CTAs per SM overlap each other's phases.
+// CTA = one M tile of 128 w-positions x ht rows; it owns (batch, h-block, w-block, Cout-tile) and
+// walks the depth axis, so every input byte is fetched (1 + 2/ht) times from L2 and the packed
+// weights are staged once per CTA.  Warp-specialised pipeline, mbarrier-synchronised:
+//   warps 4-7  producers : cp.async (16 B, zero-fill for the halo) input depth-slabs into a ring
+//   warp  8    MMA issuer: one thread walks the op table, tcgen05.mma -> TMEM, tcgen05.commit
+//   warps 0-3  epilogue  : tcgen05.ld (32x32b) -> folded-BN affine + ReLU + skip -> C8 bf16 store
+//                          (or fp32 logits for the Cout = 1 `prob` layer)
+// The accumulators are double-buffered in TMEM, so step s+1's MMAs overlap step s's epilogue, and
+// the ring holds one step of prefetch, so the loads of step s+1 overlap both.
 #include <vector>
 
 #include "common.cuh"
 
 namespace mvs {
 
-constexpr int UM_THREADS = 128;
+constexpr int UM_EPI_THREADS = 128;
+constexpr int UM_PROD_THREADS = 128;
+constexpr int UM_THREADS = UM_EPI_THREADS + UM_PROD_THREADS + 32;
 constexpr int UM_COLS = 132;        // staged columns per row (128 + halo + pairing pad)
 constexpr int UM_MAX_OPS = 224;
 constexpr int UM_MAX_ACC = 16;
 constexpr int UM_MAX_KSTEPS = 112;
+constexpr int UM_MAX_RING = 6;
 
 enum UmMode { UM_CONV_S1 = 0, UM_CONV_S2 = 1, UM_DECONV_S2 = 2 };
 
 struct MmaOp {                // offsets in 16-byte units
     uint16_t a_off;           // within a depth slab
     uint16_t b_off;           // within the packed weights of this Cout tile
-    uint8_t a_lbo;            // A leading-byte-offset (distance between the two 8-channel K chunks)
-    uint8_t rd;               // which depth slab of the step (0..2)
+    uint16_t a_lbo;           // A leading-byte-offset (distance between the two 8-channel K chunks)
     uint8_t acc;              // accumulator index
-    uint8_t first;            // 1: overwrite the accumulator (first k-step of this step)
+    uint8_t rd_first;         // bits 0-1: depth slab of the step (0..2); bit 7: overwrite the accumulator
 };
 
 struct AccOut {               // where accumulator `acc` lands: od = od_mul*step + dd, oh = oh_mul*(h0+th) + dh
@@ -57,9 +62,9 @@ struct ConvPlan {
     int B, D, H, W, Do, Ho, Wo;
     int cin_chunks, cout, cout_chunks, n, cout_tiles;
     int mode, ht, rh, arr, rd, ring;
-    int slab_units, weight_units, tmem_cols;
+    int slab_units, weight_units, tmem_cols, acc_cols;
     int h_mul, h_base;        // h_in(r) = h_mul * h0 + h_base + r          (h0 = ht * blockIdx.y)
-    int d_mul, d_base;        // d_in(step, k) = d_mul * step + d_base + k
+    int d_mul, d_base;        // d_in(slab i) = d_base + i ; step s uses slabs d_mul*s + {0..rd-1}
     int w_step, w_base[2];    // w_in(arr, col) = w_step * (m0 + col) + w_base[arr]
     int od_mul, oh_mul, w_mul;
     int n_ops, n_acc, steps;
@@ -114,6 +119,11 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -140,6 +150,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 {
@@ -169,8 +186,12 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4 *sw = reinterpret_cast<uint4 *>(smem_raw);                 // packed weights of this Cout tile
     uint4 *sa = sw + P.weight_units;                                 // ring of depth slabs
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sa + (size_t)P.ring * P.slab_units);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sa + (size_t)P.ring * P.slab_units);
+    uint64_t *full = bars;                       // [ring]  slab landed            (128 producer arrivals)
+    uint64_t *empty = bars + UM_MAX_RING;        // [ring]  slab no longer read     (1 tcgen05.commit)
+    uint64_t *tfull = bars + 2 * UM_MAX_RING;    // [2]     accumulators complete   (1 tcgen05.commit)
+    uint64_t *tempty = tfull + 2;                // [2]     accumulators drained    (128 epilogue arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128;
@@ -178,127 +199,153 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     const int b = blockIdx.z / P.cout_tiles, ct = blockIdx.z % P.cout_tiles;
 
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
-    if (tid == 0) {
-        mbar_init(mbar, 1);
+    if (tid == 32) {
+        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, UM_PROD_THREADS); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, UM_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    // weights: staged once per CTA
-    {
+    {   // weights: staged once per CTA
         const uint4 *src = wpk + (size_t)ct * P.weight_units;
         for (int i = tid; i < P.weight_units; i += UM_THREADS) sw[i] = __ldg(src + i);
     }
+    fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = *tmem_slot;
-    const uint32_t sw_addr = smem_u32(sw), sa_addr = smem_u32(sa);
-    const uint32_t idesc = umma_idesc_bf16(128, P.n);
+    const int n_slabs = P.d_mul * (P.steps - 1) + P.rd;              // depth slabs this CTA stages in total
 
-    const int lines = P.rh * P.cin_chunks * P.arr;                    // staged lines of UM_COLS vectors per slab
-    const size_t plane_in = (size_t)P.H * P.W;
-    int d_staged = -(1 << 30);                                       // highest input depth already in the ring
-    uint32_t parity = 0;
-
-    for (int step = 0; step < P.steps; ++step) {
-        // ---- stage the depth slabs this step needs and the ring does not hold yet ----
-        for (int k = 0; k < P.rd; ++k) {
-            const int d_in = P.d_mul * step + P.d_base + k;
-            if (d_in <= d_staged) continue;
-            uint4 *slab = sa + (size_t)((d_in + 3 * P.ring) % P.ring) * P.slab_units;
+    if (warp >= 4 && warp < 8) {
+        // =========================== producers: global -> shared (cp.async) ===========================
+        const int pwarp = warp - 4;
+        const int lines = P.rh * P.cin_chunks * P.arr;                // lines of UM_COLS 16-byte vectors per slab
+        const size_t plane_in = (size_t)P.H * P.W;
+        for (int i = 0; i < n_slabs; ++i) {
+            const int slot = i % P.ring, q = i / P.ring;
+            if (q >= 1) mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
+            const int d_in = P.d_base + i;
             const bool d_ok = d_in >= 0 && d_in < P.D;
-            for (int ln = warp; ln < lines; ln += UM_THREADS / 32) {
+            uint4 *slab = sa + (size_t)slot * P.slab_units;
+            for (int ln = pwarp; ln < lines; ln += UM_PROD_THREADS / 32) {
                 const int a = ln % P.arr, chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
                 const int h_in = P.h_mul * h0 + P.h_base + r;
                 const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
                 const uint4 *src = x + (((size_t)b * P.cin_chunks + chunk) * P.D + (row_ok ? d_in : 0)) * plane_in +
                                    (size_t)(row_ok ? h_in : 0) * P.W;
                 uint4 *dst = slab + (size_t)ln * UM_COLS;
-                for (int c = lane; c < UM_COLS; c += 32) {
-                    const int w_in = P.w_step * (m0 + c) + P.w_base[a];
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (row_ok && w_in >= 0 && w_in < P.W) v = __ldg(src + w_in);
-                    dst[c] = v;
+                const int wb = P.w_step * m0 + P.w_base[a];
+#pragma unroll
+                for (int cc = 0; cc < (UM_COLS + 31) / 32; ++cc) {
+                    const int c = cc * 32 + lane;
+                    if (c < UM_COLS) {
+                        const int w_in = P.w_step * c + wb;
+                        const bool ok = row_ok && w_in >= 0 && w_in < P.W;
+                        cp_async16(dst + c, src + (ok ? w_in : 0), ok ? 16u : 0u);
+                    }
                 }
             }
-            d_staged = d_in;
+            cp_async_commit();
+            if (i >= 1) {              // slab i-1 has landed for this thread: publish it
+                cp_async_wait<1>();
+                fence_async_smem();
+                mbar_arrive(full + (i - 1) % P.ring);
+            }
         }
-        fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-
-        // ---- one thread issues the whole MMA table of this step ----
-        if (tid == 0) {
-            tc_fence_after();
-            uint32_t slab_addr[3];
+        cp_async_wait<0>();
+        fence_async_smem();
+        mbar_arrive(full + (n_slabs - 1) % P.ring);
+    } else if (warp == 8) {
+        // =========================== MMA issuer: one thread ===========================================
+        if (lane == 0) {
+            const uint32_t sw_addr = smem_u32(sw), sa_addr = smem_u32(sa);
+            const uint32_t idesc = umma_idesc_bf16(128, P.n);
+            int waited = 0;
+            for (int step = 0; step < P.steps; ++step) {
+                const int first = P.d_mul * step;
+                while (waited < first + P.rd) {
+                    mbar_wait(full + waited % P.ring, (uint32_t)(waited / P.ring) & 1u);
+                    ++waited;
+                }
+                const int buf = step & 1, use = step >> 1;
+                if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
+                tc_fence_after();
+                uint32_t slab_addr[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int d_in = P.d_mul * step + P.d_base + k;
-                slab_addr[k] = sa_addr + (uint32_t)(((d_in + 3 * P.ring) % P.ring) * P.slab_units) * 16u;
+                for (int k = 0; k < 3; ++k) slab_addr[k] = sa_addr + (uint32_t)(((first + k) % P.ring) * P.slab_units) * 16u;
+                const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
+                for (int i = 0; i < P.n_ops; ++i) {
+                    const MmaOp op = P.ops[i];
+                    const uint64_t ad = umma_smem_desc(slab_addr[op.rd_first & 3] + (uint32_t)op.a_off * 16u, op.a_lbo, 8);
+                    const uint64_t bd = umma_smem_desc(sw_addr + (uint32_t)op.b_off * 16u, (uint32_t)P.n, 8);
+                    umma_bf16_ss(tbase + (uint32_t)op.acc * (uint32_t)P.n, ad, bd, idesc, (op.rd_first & 0x80) ? 0u : 1u);
+                }
+                // slabs the next step no longer reads go back to the producers once these MMAs retire
+                for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + (first + k) % P.ring);
+                umma_commit(tfull + buf);
             }
-            for (int i = 0; i < P.n_ops; ++i) {
-                const MmaOp op = P.ops[i];
-                const uint64_t ad = umma_smem_desc(slab_addr[op.rd] + (uint32_t)op.a_off * 16u, op.a_lbo, 8);
-                const uint64_t bd = umma_smem_desc(sw_addr + (uint32_t)op.b_off * 16u, (uint32_t)P.n, 8);
-                umma_bf16_ss(taddr + (uint32_t)op.acc * (uint32_t)P.n, ad, bd, idesc, op.first ? 0u : 1u);
-            }
-            umma_commit(mbar);
         }
-        mbar_wait(mbar, parity);
-        parity ^= 1u;
-        tc_fence_after();
-
-        // ---- epilogue: TMEM -> registers -> affine/ReLU/skip -> global ----
+    } else if (warp < 4) {
+        // =========================== epilogue: TMEM -> registers -> global ============================
         const int m = warp * 32 + lane;                               // row of the M tile owned by this thread
-        for (int a = 0; a < P.n_acc; ++a) {
-            const AccOut ao = P.acc[a];
-            const int od = P.od_mul * step + ao.dd;
-            const int oh = P.oh_mul * (h0 + ao.th) + ao.dh;
-            const int ow = P.w_mul * (m0 + m) + ao.wadd;
-            const bool ok = od < P.Do && oh < P.Ho && ow < P.Wo;      // warp-uniform except for ow
-            for (int n0 = 0; n0 < P.n; n0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * P.n + n0), v);
-                const int c0 = ct * P.n + n0;
-                if (!ok || c0 >= P.cout) continue;
-                if (P.out_f32) {
-                    float o = v[0] * (scale ? __ldg(scale) : 1.f) + (shift ? __ldg(shift) : 0.f);
-                    if (P.relu) o = fmaxf(o, 0.f);
-                    reinterpret_cast<float *>(y)[(((size_t)b * P.Do + od) * P.Ho + oh) * P.Wo + ow] = o;
-                    continue;
-                }
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int cc = c0 + half * 8;
-                    if (cc >= P.cout_chunks * 8) break;
-                    float o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = cc + e;
-                        const float sc = (scale && c < P.cout) ? __ldg(scale + c) : 1.f;
-                        const float sh = (shift && c < P.cout) ? __ldg(shift + c) : 0.f;
-                        float t = fmaf(v[half * 8 + e], sc, sh);
-                        if (P.relu) t = fmaxf(t, 0.f);
-                        o[e] = c < P.cout ? t : 0.f;
+        const uint32_t lane_base = taddr + ((uint32_t)(warp * 32) << 16);
+        for (int step = 0; step < P.steps; ++step) {
+            const int buf = step & 1, use = step >> 1;
+            mbar_wait(tfull + buf, (uint32_t)use & 1u);
+            tc_fence_after();
+            for (int a = 0; a < P.n_acc; ++a) {
+                const AccOut ao = P.acc[a];
+                const int od = P.od_mul * step + ao.dd;
+                const int oh = P.oh_mul * (h0 + ao.th) + ao.dh;
+                const int ow = P.w_mul * (m0 + m) + ao.wadd;
+                const bool ok = od < P.Do && oh < P.Ho && ow < P.Wo;
+                for (int n0 = 0; n0 < P.n; n0 += 16) {
+                    float v[16];
+                    tmem_ld16(lane_base + (uint32_t)(buf * P.acc_cols + a * P.n + n0), v);
+                    const int c0 = ct * P.n + n0;
+                    if (!ok || c0 >= P.cout) continue;
+                    if (P.out_f32) {
+                        float o = v[0] * (scale ? __ldg(scale) : 1.f) + (shift ? __ldg(shift) : 0.f);
+                        if (P.relu) o = fmaxf(o, 0.f);
+                        reinterpret_cast<float *>(y)[(((size_t)b * P.Do + od) * P.Ho + oh) * P.Wo + ow] = o;
+                        continue;
                     }
-                    const size_t oidx = ((((size_t)b * P.cout_chunks + (cc >> 3)) * P.Do + od) * P.Ho + oh) * P.Wo + ow;
-                    if (P.has_skip) {
-                        const uint4 s = __ldg(skip + oidx);
-                        const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            o[2 * e] += __uint_as_float(sv[e] << 16);
-                            o[2 * e + 1] += __uint_as_float(sv[e] & 0xffff0000u);
+                    for (int half = 0; half < 2; ++half) {
+                        const int cc = c0 + half * 8;
+                        if (cc >= P.cout_chunks * 8) break;
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = cc + e;
+                            const float sc = (scale && c < P.cout) ? __ldg(scale + c) : 1.f;
+                            const float sh = (shift && c < P.cout) ? __ldg(shift + c) : 0.f;
+                            float t = fmaf(v[half * 8 + e], sc, sh);
+                            if (P.relu) t = fmaxf(t, 0.f);
+                            o[e] = c < P.cout ? t : 0.f;
                         }
+                        const size_t oidx = ((((size_t)b * P.cout_chunks + (cc >> 3)) * P.Do + od) * P.Ho + oh) * P.Wo + ow;
+                        if (P.has_skip) {
+                            const uint4 s = __ldg(skip + oidx);
+                            const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                o[2 * e] += __uint_as_float(sv[e] << 16);
+                                o[2 * e + 1] += __uint_as_float(sv[e] & 0xffff0000u);
+                            }
+                        }
+                        uint4 pk;
+                        pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+                        pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+                        reinterpret_cast<uint4 *>(y)[oidx] = pk;
                     }
-                    uint4 pk;
-                    pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-                    pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-                    reinterpret_cast<uint4 *>(y)[oidx] = pk;
                 }
             }
+            tc_fence_before();         // this thread's TMEM reads are complete (tcgen05.wait::ld) ...
+            mbar_arrive(tempty + buf); // ... so the issuer may overwrite the buffer
         }
-        tc_fence_before();             // TMEM reads done before the next step's MMAs overwrite the accumulators
-        __syncthreads();
     }
+    tc_fence_before();
+    __syncthreads();
     if (warp == 0) tmem_dealloc(taddr, (uint32_t)P.tmem_cols);
 }
 
@@ -344,7 +391,9 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
     g.mode = transposed ? (stride == 2 ? UM_DECONV_S2 : UM_CONV_S1) : (stride == 2 ? UM_CONV_S2 : UM_CONV_S1);
     g.cin_chunks = (Cin + 7) / 8;
     const int n_full = round_up(Cout, 16);
-    g.n = n_full > 32 ? 32 : n_full;                // Cout tiles of <= 32 keep the packed weights within smem
+    // Cout tiles keep (packed weights + slab ring) within shared memory: <= 32 wide, 16 for Cin >= 64
+    const int n_cap = g.cin_chunks >= 8 ? 16 : 32;
+    g.n = n_full > n_cap ? n_cap : n_full;
     g.cout_tiles = (n_full + g.n - 1) / g.n;
     g.arr = g.mode == UM_CONV_S2 ? 2 : 1;
     const int CH = g.cin_chunks;
@@ -401,9 +450,15 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
     return g;
 }
 
+static size_t plan_smem_bytes(int weight_units, int ring, int slab_units)
+{
+    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16;
+}
+
 static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
                        int transposed, int flags, bool out_f32, bool has_skip, size_t &smem_bytes)
 {
+    (void)Cin; (void)stride; (void)transposed;
     memset(&P, 0, sizeof(P));
     P.B = B; P.D = D; P.H = H; P.W = W;
     const bool deconv = g.mode == UM_DECONV_S2;
@@ -414,45 +469,47 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     P.mode = g.mode; P.arr = g.arr;
     P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip;
     const int S = g.mode == UM_CONV_S2 ? 2 : 1;
-    const int per_row_ks = deconv ? 0 : (int)g.ks.size();
     const int acc_per_row = deconv ? 8 : 1;
-    const int ops_per_row = deconv ? (int)g.ks.size() : per_row_ks;
+    const int ops_per_row = (int)g.ks.size();
     P.weight_units = (int)g.ks.size() * 2 * g.n;
     P.rd = deconv ? 2 : 3;
-    P.ring = P.rd;
+    P.d_mul = deconv ? 1 : S;
     const int rows_h = deconv ? H : P.Ho;
-    // choose ht: as many rows as the op table / TMEM / shared memory allow, preferring 2 CTAs per SM
-    int best = 0;
-    for (int pass = 0; pass < 2 && !best; ++pass) {
-        const size_t budget = pass == 0 ? 110 * 1024 : 225 * 1024;
+    // ht (rows per CTA) and ring depth: prefer one full step of prefetch and two CTAs per SM, then relax.
+    int best = 0, best_ring = 0;
+    for (int pass = 0; pass < 3 && !best; ++pass) {
+        const size_t budget = pass == 0 ? 112 * 1024 : 226 * 1024;
+        const int ring = pass < 2 ? P.rd + P.d_mul : P.rd;
         for (int ht = 8; ht >= 1; --ht) {
             if (ht > rows_h && ht > 1) continue;
-            if (ht * ops_per_row > UM_MAX_OPS || ht * acc_per_row > UM_MAX_ACC || ht * acc_per_row * g.n > 512) continue;
+            // TMEM: two accumulator buffers per CTA; with two CTAs per SM (pass 0) each may take half of the 512 columns
+            if (ht * ops_per_row > UM_MAX_OPS || ht * acc_per_row > UM_MAX_ACC ||
+                2 * ht * acc_per_row * g.n > (pass == 0 ? 256 : 512)) continue;
             const int rh = deconv ? ht + 1 : S * (ht - 1) + 3;
-            const size_t bytes = ((size_t)P.weight_units + (size_t)P.ring * rh * g.cin_chunks * g.arr * UM_COLS) * 16 + 64;
-            if (bytes > budget) continue;
-            best = ht;
+            if (plan_smem_bytes(P.weight_units, ring, rh * g.cin_chunks * g.arr * UM_COLS) > budget) continue;
+            best = ht; best_ring = ring;
             break;
         }
     }
     if (!best) return false;
     P.ht = best;
+    P.ring = best_ring;
     P.rh = deconv ? P.ht + 1 : S * (P.ht - 1) + 3;
     P.slab_units = P.rh * g.cin_chunks * g.arr * UM_COLS;
-    smem_bytes = ((size_t)P.weight_units + (size_t)P.ring * P.slab_units) * 16 + 64;
+    smem_bytes = plan_smem_bytes(P.weight_units, P.ring, P.slab_units);
     P.n_acc = P.ht * acc_per_row;
+    P.acc_cols = P.n_acc * g.n;
     int cols = 32;
-    while (cols < P.n_acc * g.n) cols *= 2;
+    while (cols < 2 * P.acc_cols) cols *= 2;
     P.tmem_cols = cols;
     if (deconv) {
-        P.h_mul = 1; P.h_base = 0; P.d_mul = 1; P.d_base = 0; P.w_step = 1; P.w_base[0] = 0; P.w_base[1] = 0;
+        P.h_mul = 1; P.h_base = 0; P.d_base = 0; P.w_step = 1; P.w_base[0] = 0; P.w_base[1] = 0;
         P.od_mul = 2; P.oh_mul = 2; P.w_mul = 2; P.steps = D;
     } else {
-        P.h_mul = S; P.h_base = -1; P.d_mul = S; P.d_base = -1; P.w_step = S;
+        P.h_mul = S; P.h_base = -1; P.d_base = -1; P.w_step = S;
         P.w_base[0] = S == 1 ? -1 : 0; P.w_base[1] = -1;
         P.od_mul = 1; P.oh_mul = 1; P.w_mul = 1; P.steps = P.Do;
     }
-    const int plane = g.arr * UM_COLS;
     int n_ops = 0;
     for (int th = 0; th < P.ht; ++th) {
         bool seen[8] = {false, false, false, false, false, false, false, false};
@@ -460,14 +517,14 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             const KStep &ks = g.ks[k];
             MmaOp op;
             const int row = S * th + ks.rh;
-            op.a_off = (uint16_t)(((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col);
+            const int a_off = ((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col;
+            op.a_off = (uint16_t)a_off;
             op.b_off = (uint16_t)(k * 2 * g.n);
-            op.a_lbo = (uint8_t)ks.lbo;
-            op.rd = (uint8_t)ks.rd;
+            op.a_lbo = (uint16_t)ks.lbo;
             op.acc = (uint8_t)(th * acc_per_row + ks.cls);
-            op.first = seen[ks.cls] ? 0 : 1;
+            op.rd_first = (uint8_t)(ks.rd | (seen[ks.cls] ? 0 : 0x80));
             seen[ks.cls] = true;
-            if (ks.lbo > 255 || (int)op.a_off != ((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col) return false;
+            if (ks.lbo > 0x3FFF || a_off > 0xFFFF || k * 2 * g.n > 0xFFFF) return false;
             P.ops[n_ops++] = op;
         }
         for (int c = 0; c < acc_per_row; ++c) {
@@ -478,7 +535,6 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             ao.wadd = deconv ? (int8_t)(c & 1) : 0;
         }
     }
-    (void)plane;
     P.n_ops = n_ops;
     return true;
 }
