@@ -105,7 +105,7 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t a_desc, u
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+        :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
 }
 
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
@@ -192,6 +192,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     uint64_t *tfull = bars + 2 * UM_MAX_RING;    // [2]     accumulators complete   (1 tcgen05.commit)
     uint64_t *tempty = tfull + 2;                // [2]     accumulators drained    (128 epilogue arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint4 *sops = reinterpret_cast<uint4 *>(tmem_slot + 4);          // [n_ops] issue-ready op table
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128;
@@ -208,6 +209,19 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const uint4 *src = wpk + (size_t)ct * P.weight_units;
         for (int i = tid; i < P.weight_units; i += UM_THREADS) sw[i] = __ldg(src + i);
     }
+    {   // issue-ready op table: everything that does not depend on the step is folded in here, so the
+        // single issuing thread spends ~8 instructions per MMA instead of a chain of dependent loads
+        const uint32_t sw_units = smem_u32(sw) >> 4;
+        for (int i = tid; i < P.n_ops; i += UM_THREADS) {
+            const MmaOp op = P.ops[i];
+            uint4 e;
+            e.x = (uint32_t)op.a_off | ((uint32_t)op.a_lbo << 16);                       // + slab base (16 B units)
+            e.y = ((sw_units + (uint32_t)op.b_off) & 0x3FFFu) | ((uint32_t)P.n << 16);     // B descriptor, low word
+            e.z = (uint32_t)op.acc * (uint32_t)P.n;                                        // accumulator column
+            e.w = (uint32_t)op.rd_first;
+            sops[i] = e;
+        }
+    }
     fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -220,9 +234,20 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int pwarp = warp - 4;
         const int lines = P.rh * P.cin_chunks * P.arr;                // lines of UM_COLS 16-byte vectors per slab
         const size_t plane_in = (size_t)P.H * P.W;
+        int pending = -1;              // slab staged (cp.async committed) but not yet published
         for (int i = 0; i < n_slabs; ++i) {
             const int slot = i % P.ring, q = i / P.ring;
-            if (q >= 1) mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
+            if (q >= 1) {
+                // never block on `empty` while holding an unpublished slab: the issuer may need it to
+                // retire the very slab we are waiting for (ring == rd leaves no slack)
+                if (pending >= 0) {
+                    cp_async_wait<0>();
+                    fence_async_smem();
+                    mbar_arrive(full + pending % P.ring);
+                    pending = -1;
+                }
+                mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
+            }
             const int d_in = P.d_base + i;
             const bool d_ok = d_in >= 0 && d_in < P.D;
             uint4 *slab = sa + (size_t)slot * P.slab_units;
@@ -245,19 +270,22 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 }
             }
             cp_async_commit();
-            if (i >= 1) {              // slab i-1 has landed for this thread: publish it
+            if (pending >= 0) {        // the previous slab has landed for this thread: publish it
                 cp_async_wait<1>();
                 fence_async_smem();
-                mbar_arrive(full + (i - 1) % P.ring);
+                mbar_arrive(full + pending % P.ring);
             }
+            pending = i;
         }
-        cp_async_wait<0>();
-        fence_async_smem();
-        mbar_arrive(full + (n_slabs - 1) % P.ring);
+        if (pending >= 0) {
+            cp_async_wait<0>();
+            fence_async_smem();
+            mbar_arrive(full + pending % P.ring);
+        }
     } else if (warp == 8) {
         // =========================== MMA issuer: one thread ===========================================
         if (lane == 0) {
-            const uint32_t sw_addr = smem_u32(sw), sa_addr = smem_u32(sa);
+            const uint32_t sa_addr = smem_u32(sa);
             const uint32_t idesc = umma_idesc_bf16(128, P.n);
             int waited = 0;
             for (int step = 0; step < P.steps; ++step) {
@@ -269,15 +297,33 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 const int buf = step & 1, use = step >> 1;
                 if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
                 tc_fence_after();
-                uint32_t slab_addr[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) slab_addr[k] = sa_addr + (uint32_t)(((first + k) % P.ring) * P.slab_units) * 16u;
+                const uint32_t sa_units = sa_addr >> 4;
+                const uint32_t s0 = sa_units + (uint32_t)(((first + 0) % P.ring) * P.slab_units);
+                const uint32_t s1 = sa_units + (uint32_t)(((first + 1) % P.ring) * P.slab_units);
+                const uint32_t s2 = sa_units + (uint32_t)(((first + 2) % P.ring) * P.slab_units);
                 const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
-                for (int i = 0; i < P.n_ops; ++i) {
-                    const MmaOp op = P.ops[i];
-                    const uint64_t ad = umma_smem_desc(slab_addr[op.rd_first & 3] + (uint32_t)op.a_off * 16u, op.a_lbo, 8);
-                    const uint64_t bd = umma_smem_desc(sw_addr + (uint32_t)op.b_off * 16u, (uint32_t)P.n, 8);
-                    umma_bf16_ss(tbase + (uint32_t)op.acc * (uint32_t)P.n, ad, bd, idesc, (op.rd_first & 0x80) ? 0u : 1u);
+                constexpr uint32_t kDescHi = 8u | (1u << 14);       // SBO = 8 units (128 B) | version = 1 (bit 46)
+                int i = 0;
+                for (; i + 4 <= P.n_ops; i += 4) {
+                    uint4 e[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) e[j] = sops[i + j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t rd = e[j].w & 3u;
+                        const uint32_t base = rd == 0 ? s0 : (rd == 1 ? s1 : s2);
+                        const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e[j].x + base) & 0x3FFF3FFFu);
+                        const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)e[j].y;
+                        umma_bf16_ss(tbase + e[j].z, ad, bd, idesc, (e[j].w & 0x80u) ? 0u : 1u);
+                    }
+                }
+                for (; i < P.n_ops; ++i) {
+                    const uint4 e = sops[i];
+                    const uint32_t rd = e.w & 3u;
+                    const uint32_t base = rd == 0 ? s0 : (rd == 1 ? s1 : s2);
+                    const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e.x + base) & 0x3FFF3FFFu);
+                    const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)e.y;
+                    umma_bf16_ss(tbase + e.z, ad, bd, idesc, (e.w & 0x80u) ? 0u : 1u);
                 }
                 // slabs the next step no longer reads go back to the producers once these MMAs retire
                 for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + (first + k) % P.ring);
@@ -452,7 +498,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
 
 static size_t plan_smem_bytes(int weight_units, int ring, int slab_units)
 {
-    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16;
+    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16 + UM_MAX_OPS * 16;
 }
 
 static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
@@ -510,22 +556,23 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         P.w_base[0] = S == 1 ? -1 : 0; P.w_base[1] = -1;
         P.od_mul = 1; P.oh_mul = 1; P.w_mul = 1; P.steps = P.Do;
     }
-    int n_ops = 0;
+    // ops per accumulator, then emitted round-robin so that consecutive MMAs target different TMEM
+    // accumulators (independent chains pipeline in the tensor core; a single chain serialises)
+    std::vector<std::vector<MmaOp>> per_acc((size_t)P.n_acc);
     for (int th = 0; th < P.ht; ++th) {
-        bool seen[8] = {false, false, false, false, false, false, false, false};
         for (size_t k = 0; k < g.ks.size(); ++k) {
             const KStep &ks = g.ks[k];
             MmaOp op;
             const int row = S * th + ks.rh;
             const int a_off = ((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col;
+            const int acc = th * acc_per_row + ks.cls;
             op.a_off = (uint16_t)a_off;
             op.b_off = (uint16_t)(k * 2 * g.n);
             op.a_lbo = (uint16_t)ks.lbo;
-            op.acc = (uint8_t)(th * acc_per_row + ks.cls);
-            op.rd_first = (uint8_t)(ks.rd | (seen[ks.cls] ? 0 : 0x80));
-            seen[ks.cls] = true;
+            op.acc = (uint8_t)acc;
+            op.rd_first = (uint8_t)(ks.rd | (per_acc[acc].empty() ? 0x80 : 0));
             if (ks.lbo > 0x3FFF || a_off > 0xFFFF || k * 2 * g.n > 0xFFFF) return false;
-            P.ops[n_ops++] = op;
+            per_acc[acc].push_back(op);
         }
         for (int c = 0; c < acc_per_row; ++c) {
             AccOut &ao = P.acc[th * acc_per_row + c];
@@ -534,6 +581,13 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             ao.dh = deconv ? (int8_t)((c >> 1) & 1) : 0;
             ao.wadd = deconv ? (int8_t)(c & 1) : 0;
         }
+    }
+    int n_ops = 0;
+    for (size_t j = 0;; ++j) {
+        bool any = false;
+        for (auto &v : per_acc)
+            if (j < v.size()) { P.ops[n_ops++] = v[j]; any = true; }
+        if (!any) break;
     }
     P.n_ops = n_ops;
     return true;
