@@ -283,8 +283,54 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             mbar_arrive(full + pending % P.ring);
         }
     } else if (warp == 8) {
-        // =========================== MMA issuer: one thread ===========================================
-        if (lane == 0) {
+        // =========================== MMA issuer ========================================================
+        // The whole warp walks the op table on warp-uniform values (kernel-parameter table, loop counters),
+        // so descriptors are built in the uniform datapath; only the tcgen05 instructions themselves are
+        // predicated on one elected lane.  (Issuing from inside `if (lane == 0)` makes the compiler wrap
+        // every UTCHMMA in an R2UR waterfall loop: ~100 cycles per MMA.)
+        {
+            uint32_t leader;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
+            const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
+            const uint32_t idesc = umma_idesc_bf16(128, P.n);
+            constexpr uint32_t kDescHi = 8u | (1u << 14);           // SBO = 8 units (128 B) | version = 1 (bit 46)
+            const uint32_t b_hi16 = (uint32_t)P.n << 16;            // B LBO = N units
+            int waited = 0;
+            for (int step = 0; step < P.steps; ++step) {
+                const int first = P.d_mul * step;
+                while (waited < first + P.rd) {
+                    mbar_wait(full + waited % P.ring, (uint32_t)(waited / P.ring) & 1u);
+                    ++waited;
+                }
+                const int buf = step & 1, use = step >> 1;
+                if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
+                tc_fence_after();
+                const uint32_t s0 = sa_units + (uint32_t)(((first + 0) % P.ring) * P.slab_units);
+                const uint32_t s1 = sa_units + (uint32_t)(((first + 1) % P.ring) * P.slab_units);
+                const uint32_t s2 = sa_units + (uint32_t)(((first + 2) % P.ring) * P.slab_units);
+                const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
+#pragma unroll 4
+                for (int i = 0; i < P.n_ops; ++i) {
+                    const MmaOp op = P.ops[i];
+                    const uint32_t rd = op.rd_first & 3u;
+                    const uint32_t base = rd == 0 ? s0 : (rd == 1 ? s1 : s2);
+                    const uint32_t a_lo = ((base + op.a_off) & 0x3FFFu) | ((uint32_t)op.a_lbo << 16);
+                    const uint32_t b_lo = ((sw_units + op.b_off) & 0x3FFFu) | b_hi16;
+                    const uint64_t ad = ((uint64_t)kDescHi << 32) | a_lo;
+                    const uint64_t bd = ((uint64_t)kDescHi << 32) | b_lo;
+                    const uint32_t dcol = tbase + (uint32_t)op.acc * (uint32_t)P.n;
+                    const uint32_t accum = (op.rd_first & 0x80u) ? 0u : 1u;
+                    if (leader) umma_bf16_ss(dcol, ad, bd, idesc, accum);
+                }
+                if (leader) {
+                    // slabs the next step no longer reads go back to the producers once these MMAs retire
+                    for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + (first + k) % P.ring);
+                    umma_commit(tfull + buf);
+                }
+                __syncwarp();
+            }
+        }
+        if (false) {
             const uint32_t sa_addr = smem_u32(sa);
             const uint32_t idesc = umma_idesc_bf16(128, P.n);
             int waited = 0;

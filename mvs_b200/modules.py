@@ -257,6 +257,20 @@ def build_cost_volume(ref_fea, src_feas: Sequence[torch.Tensor], ref_proj, src_p
     return ops.cost_volume(ref_fea, list(src_feas), list(rots), list(transs), depth_values, flags)
 
 
+def build_cost_volume_c8(ref_fea, src_feas: Sequence[torch.Tensor], ref_proj, src_projs: Sequence[torch.Tensor],
+                         depth_values, flags: int = 0):
+    """Fast-path builder: feature maps (NCHW fp32/bf16, or already C8 bf16 [B,CB,h,w,8]) -> C8 bf16
+    variance volume [B,CB,D,h,w,8] for the tensor-core CostRegNet."""
+    rots, transs = zip(*(ops.relative_pose(sp, ref_proj) for sp in src_projs))
+    as_c8 = lambda t: t if (t.dim() == 5 and t.dtype == torch.bfloat16 and t.shape[-1] == 8) else ops.pack_c8(t)
+    return ops.cost_volume_c8(as_c8(ref_fea), [as_c8(s) for s in src_feas], list(rots), list(transs), depth_values,
+                              flags)
+
+
+def _is_fast(cost_regularization) -> bool:
+    return getattr(cost_regularization, "mode", "strict") == "fast"
+
+
 def regress(cost_reg, depth_values, clamp_index):
     """softmax + depth_regression + photometric confidence on [B,1,D,h,w] or [B,D,h,w] logits."""
     logits = cost_reg.squeeze(1) if cost_reg.dim() == 5 else cost_reg
@@ -269,7 +283,8 @@ def mvsnet_hot_path(features: List[torch.Tensor], proj_matrices, depth_values, c
     features: list of [B,32,h,w]; proj_matrices [B,N,4,4]; depth_values [B,D]."""
     projs = torch.unbind(proj_matrices, 1)
     assert len(features) == len(projs), "Different number of images and projection matrices"
-    var = build_cost_volume(features[0], features[1:], projs[0], projs[1:], depth_values)
+    build = build_cost_volume_c8 if _is_fast(cost_regularization) else build_cost_volume
+    var = build(features[0], features[1:], projs[0], projs[1:], depth_values)
     depth, conf = regress(cost_regularization(var), depth_values, clamp_index=False)
     return {"depth": depth, "photometric_confidence": conf}
 
@@ -288,7 +303,8 @@ class DepthNet(nn.Module):
                 q = p[:, 0].clone()
                 q[:, :3, :4] = torch.matmul(p[:, 1, :3, :3], p[:, 0, :3, :4])
             fused.append(q)
-        var = build_cost_volume(features[0], features[1:], fused[0], fused[1:], depth_values)
+        build = build_cost_volume_c8 if _is_fast(cost_regularization) else build_cost_volume
+        var = build(features[0], features[1:], fused[0], fused[1:], depth_values)
         cost_reg = cost_regularization(var)
         logits = cost_reg.squeeze(1)
         if prob_volume_init is not None:
@@ -306,4 +322,6 @@ def proj_cost(settings, ref_feature, src_feature, level, ref_in, src_in, ref_ex,
         ref_proj = torch.cat((torch.matmul(ref_in, ref_ex[:, 0:3, :]), last), 1)
         src_projs = [torch.cat((torch.matmul(src_in[:, s], src_ex[:, s, 0:3, :]), last), 1) for s in range(settings.nsrc)]
     srcs = [src_feature[s][level] for s in range(settings.nsrc)]
+    if getattr(settings, "mvs_mode", "strict") == "fast":
+        return build_cost_volume_c8(ref_feature, srcs, ref_proj, src_projs, depth_hypos, L.REF_SUM_SQUARED)
     return build_cost_volume(ref_feature, srcs, ref_proj, src_projs, depth_hypos, L.REF_SUM_SQUARED)

@@ -90,3 +90,23 @@ def test_costreg_fast_vs_strict(family, cin):
         assert out.shape == ref.shape
     err = (out.float().reshape(ref.shape) - ref).abs().max().item()
     assert err <= 0.03 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+
+
+def test_cas_cascade_fast_vs_golden():
+    """Full 3-stage cascade on the fast path (C8 bf16 builder + tcgen05 CostRegNet) vs the reference's
+    fp32 forward: bf16 storage => looser tolerance, stated here: depth within 2e-3 relative."""
+    from mvs_b200 import modules, cascade
+    g = cases.golden("cas_cascade"); k = cases.cascade_case()
+    regs = []
+    for i, cin in enumerate((32, 16, 8)):
+        net = modules.CostRegNet(cin, 8, mode="fast")
+        net.load_state_dict({kk: torch.from_numpy(np.asarray(v)) for kk, v in cases.costreg_state("cas", cin=cin, seed=14 + i).items()}, strict=True)
+        regs.append(net.to(DEV).eval())
+    n_views = k["feats"]["stage1"].shape[0]
+    feats = [{s: cu(k["feats"][s][v]) for s in k["feats"]} for v in range(n_views)]
+    with torch.no_grad():
+        out = cascade.cascade_hot_path(feats, {s: cu(p) for s, p in k["projs"].items()}, cu(k["depth_values"]), regs,
+                                       ndepths=k["ndepths"], img_hw=(k["H"], k["W"]))
+    for s in ("stage1", "stage2", "stage3"):
+        rel = np.abs(out[s]["depth"].cpu().numpy() - g[s + "_depth"]) / g[s + "_depth"]
+        assert rel.max() < 2e-3, (s, rel.max())
