@@ -32,7 +32,8 @@ namespace mvs {
 
 constexpr int UM_EPI_THREADS = 128;
 constexpr int UM_PROD_THREADS = 128;
-constexpr int UM_THREADS = UM_EPI_THREADS + UM_PROD_THREADS + 32;
+constexpr int UM_MAX_ISSUERS = 4;
+constexpr int UM_THREADS = UM_EPI_THREADS + UM_PROD_THREADS + 32 * UM_MAX_ISSUERS;
 constexpr int UM_COLS = 132;        // staged columns per row (128 + halo + pairing pad)
 constexpr int UM_MAX_OPS = 224;
 constexpr int UM_MAX_ACC = 16;
@@ -69,8 +70,12 @@ struct ConvPlan {
     int od_mul, oh_mul, w_mul;
     int n_ops, n_acc, steps;
     int relu, out_f32, has_skip;
-    MmaOp ops[UM_MAX_OPS];
+    int n_issuers, op_begin[UM_MAX_ISSUERS + 1];   // issuer warp j owns ops [op_begin[j], op_begin[j+1])
     AccOut acc[UM_MAX_ACC];
+    // issue-ready op table (16 B per MMA, read with one uniform constant load):
+    //   x = a_off | a_lbo << 16      (+ slab base at issue time)      y = b_off | N << 16   (+ weights base)
+    //   z = accumulator column (acc * N)                              w = rd (bits 0-1) | first (bit 7)
+    uint4 ops[UM_MAX_OPS];
 };
 
 struct PackPlan {
@@ -192,7 +197,6 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     uint64_t *tfull = bars + 2 * UM_MAX_RING;    // [2]     accumulators complete   (1 tcgen05.commit)
     uint64_t *tempty = tfull + 2;                // [2]     accumulators drained    (128 epilogue arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    uint4 *sops = reinterpret_cast<uint4 *>(tmem_slot + 4);          // [n_ops] issue-ready op table
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128;
@@ -201,26 +205,13 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     if (tid == 32) {
-        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, UM_PROD_THREADS); mbar_init(empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, UM_EPI_THREADS); }
+        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, UM_PROD_THREADS); mbar_init(empty + i, (uint32_t)P.n_issuers); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, (uint32_t)P.n_issuers); mbar_init(tempty + i, UM_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     {   // weights: staged once per CTA
         const uint4 *src = wpk + (size_t)ct * P.weight_units;
         for (int i = tid; i < P.weight_units; i += UM_THREADS) sw[i] = __ldg(src + i);
-    }
-    {   // issue-ready op table: everything that does not depend on the step is folded in here, so the
-        // single issuing thread spends ~8 instructions per MMA instead of a chain of dependent loads
-        const uint32_t sw_units = smem_u32(sw) >> 4;
-        for (int i = tid; i < P.n_ops; i += UM_THREADS) {
-            const MmaOp op = P.ops[i];
-            uint4 e;
-            e.x = (uint32_t)op.a_off | ((uint32_t)op.a_lbo << 16);                       // + slab base (16 B units)
-            e.y = ((sw_units + (uint32_t)op.b_off) & 0x3FFFu) | ((uint32_t)P.n << 16);     // B descriptor, low word
-            e.z = (uint32_t)op.acc * (uint32_t)P.n;                                        // accumulator column
-            e.w = (uint32_t)op.rd_first;
-            sops[i] = e;
-        }
     }
     fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
@@ -282,19 +273,21 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             fence_async_smem();
             mbar_arrive(full + pending % P.ring);
         }
-    } else if (warp == 8) {
-        // =========================== MMA issuer ========================================================
-        // The whole warp walks the op table on warp-uniform values (kernel-parameter table, loop counters),
-        // so descriptors are built in the uniform datapath; only the tcgen05 instructions themselves are
-        // predicated on one elected lane.  (Issuing from inside `if (lane == 0)` makes the compiler wrap
-        // every UTCHMMA in an R2UR waterfall loop: ~100 cycles per MMA.)
-        {
+    } else if (warp >= 8) {
+        // =========================== MMA issuers ======================================================
+        // Up to UM_MAX_ISSUERS warps, each owning a disjoint set of accumulators (independent chains).
+        // A whole warp walks its slice of the op table on warp-uniform values (kernel-parameter table,
+        // loop counters), so descriptors are built in the uniform datapath; only the tcgen05 instructions
+        // are predicated on one elected lane.  (Issuing from inside `if (lane == 0)` makes the compiler
+        // wrap every UTCHMMA in an R2UR waterfall loop.)
+        const int iss = warp - 8;
+        if (iss < P.n_issuers) {
             uint32_t leader;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
             const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
             const uint32_t idesc = umma_idesc_bf16(128, P.n);
             constexpr uint32_t kDescHi = 8u | (1u << 14);           // SBO = 8 units (128 B) | version = 1 (bit 46)
-            const uint32_t b_hi16 = (uint32_t)P.n << 16;            // B LBO = N units
+            const int op0 = P.op_begin[iss], op1 = P.op_begin[iss + 1];
             int waited = 0;
             for (int step = 0; step < P.steps; ++step) {
                 const int first = P.d_mul * step;
@@ -310,17 +303,13 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 const uint32_t s2 = sa_units + (uint32_t)(((first + 2) % P.ring) * P.slab_units);
                 const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
 #pragma unroll 4
-                for (int i = 0; i < P.n_ops; ++i) {
-                    const MmaOp op = P.ops[i];
-                    const uint32_t rd = op.rd_first & 3u;
+                for (int i = op0; i < op1; ++i) {
+                    const uint4 e = P.ops[i];
+                    const uint32_t rd = e.w & 3u;
                     const uint32_t base = rd == 0 ? s0 : (rd == 1 ? s1 : s2);
-                    const uint32_t a_lo = ((base + op.a_off) & 0x3FFFu) | ((uint32_t)op.a_lbo << 16);
-                    const uint32_t b_lo = ((sw_units + op.b_off) & 0x3FFFu) | b_hi16;
-                    const uint64_t ad = ((uint64_t)kDescHi << 32) | a_lo;
-                    const uint64_t bd = ((uint64_t)kDescHi << 32) | b_lo;
-                    const uint32_t dcol = tbase + (uint32_t)op.acc * (uint32_t)P.n;
-                    const uint32_t accum = (op.rd_first & 0x80u) ? 0u : 1u;
-                    if (leader) umma_bf16_ss(dcol, ad, bd, idesc, accum);
+                    const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e.x + base) & 0x3FFF3FFFu);
+                    const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)((e.y + sw_units) & 0x3FFF3FFFu);
+                    if (leader) umma_bf16_ss(tbase + e.z, ad, bd, idesc, (e.w & 0x80u) ? 0u : 1u);
                 }
                 if (leader) {
                     // slabs the next step no longer reads go back to the producers once these MMAs retire
@@ -328,52 +317,6 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     umma_commit(tfull + buf);
                 }
                 __syncwarp();
-            }
-        }
-        if (false) {
-            const uint32_t sa_addr = smem_u32(sa);
-            const uint32_t idesc = umma_idesc_bf16(128, P.n);
-            int waited = 0;
-            for (int step = 0; step < P.steps; ++step) {
-                const int first = P.d_mul * step;
-                while (waited < first + P.rd) {
-                    mbar_wait(full + waited % P.ring, (uint32_t)(waited / P.ring) & 1u);
-                    ++waited;
-                }
-                const int buf = step & 1, use = step >> 1;
-                if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
-                tc_fence_after();
-                const uint32_t sa_units = sa_addr >> 4;
-                const uint32_t s0 = sa_units + (uint32_t)(((first + 0) % P.ring) * P.slab_units);
-                const uint32_t s1 = sa_units + (uint32_t)(((first + 1) % P.ring) * P.slab_units);
-                const uint32_t s2 = sa_units + (uint32_t)(((first + 2) % P.ring) * P.slab_units);
-                const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
-                constexpr uint32_t kDescHi = 8u | (1u << 14);       // SBO = 8 units (128 B) | version = 1 (bit 46)
-                int i = 0;
-                for (; i + 4 <= P.n_ops; i += 4) {
-                    uint4 e[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) e[j] = sops[i + j];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t rd = e[j].w & 3u;
-                        const uint32_t base = rd == 0 ? s0 : (rd == 1 ? s1 : s2);
-                        const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e[j].x + base) & 0x3FFF3FFFu);
-                        const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)e[j].y;
-                        umma_bf16_ss(tbase + e[j].z, ad, bd, idesc, (e[j].w & 0x80u) ? 0u : 1u);
-                    }
-                }
-                for (; i < P.n_ops; ++i) {
-                    const uint4 e = sops[i];
-                    const uint32_t rd = e.w & 3u;
-                    const uint32_t base = rd == 0 ? s0 : (rd == 1 ? s1 : s2);
-                    const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e.x + base) & 0x3FFF3FFFu);
-                    const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)e.y;
-                    umma_bf16_ss(tbase + e.z, ad, bd, idesc, (e.w & 0x80u) ? 0u : 1u);
-                }
-                // slabs the next step no longer reads go back to the producers once these MMAs retire
-                for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + (first + k) % P.ring);
-                umma_commit(tfull + buf);
             }
         }
     } else if (warp < 4) {
@@ -544,7 +487,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
 
 static size_t plan_smem_bytes(int weight_units, int ring, int slab_units)
 {
-    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16 + UM_MAX_OPS * 16;
+    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16;
 }
 
 static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
@@ -628,13 +571,26 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             ao.wadd = deconv ? (int8_t)(c & 1) : 0;
         }
     }
+    // issuer j owns accumulators {a : a % n_issuers == j}; its ops are contiguous in the table
+    P.n_issuers = P.n_acc < UM_MAX_ISSUERS ? P.n_acc : UM_MAX_ISSUERS;
     int n_ops = 0;
-    for (size_t j = 0;; ++j) {
-        bool any = false;
-        for (auto &v : per_acc)
-            if (j < v.size()) { P.ops[n_ops++] = v[j]; any = true; }
-        if (!any) break;
+    for (int iss = 0; iss < P.n_issuers; ++iss) {
+        P.op_begin[iss] = n_ops;
+        for (size_t j = 0;; ++j) {
+            bool any = false;
+            for (int a = iss; a < P.n_acc; a += P.n_issuers) {
+                const std::vector<MmaOp> &v = per_acc[(size_t)a];
+                if (j >= v.size()) continue;
+                const MmaOp &op = v[j];
+                P.ops[n_ops++] = make_uint4((uint32_t)op.a_off | ((uint32_t)op.a_lbo << 16),
+                                            (uint32_t)op.b_off | ((uint32_t)g.n << 16), (uint32_t)op.acc * (uint32_t)g.n,
+                                            (uint32_t)op.rd_first);
+                any = true;
+            }
+            if (!any) break;
+        }
     }
+    for (int iss = P.n_issuers; iss <= UM_MAX_ISSUERS; ++iss) P.op_begin[iss] = n_ops;
     P.n_ops = n_ops;
     return true;
 }
