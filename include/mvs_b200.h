@@ -41,6 +41,8 @@ extern "C" {
 #define MVS_RELU 8              /* conv epilogue: apply ReLU after the affine                    */
 #define MVS_CLAMP_INDEX 16      /* CasMVSNet/models/cas_mvsnet.py:62 depth_index.clamp(0, D-1)    */
 #define MVS_INPUT_IS_PROB 32    /* softargmin: input already soft-maxed (depth_regression(p, d)) */
+#define MVS_BLEND_BF16 64       /* C8 builder: bilinear blend in packed bf16x2 (sums / variance stay fp32) */
+#define MVS_FAST_COORDS 128     /* mvs_warp_taps: probe the C8 builder's division-free-call tap arithmetic */
 
 /* depth_mode */
 #define MVS_DEPTH_PLANE 0       /* depth [B,D]       MVSNet/models/module.py:46                   */

@@ -17,6 +17,8 @@ REF_SUM_SQUARED = 4
 RELU = 8
 CLAMP_INDEX = 16
 INPUT_IS_PROB = 32
+BLEND_BF16 = 64
+FAST_COORDS = 128
 DEPTH_PLANE = 0
 DEPTH_PIXEL = 1
 F32 = 0

@@ -229,6 +229,9 @@ warp_variance_bwd_kernel(const float *__restrict__ gout, const float *__restrict
     }
 }
 
+int warp_taps_fast(const float *rot, const float *trans, const float *depth, int depth_mode, int32_t *x0, int32_t *y0,
+                   uint8_t *mask, float *ixy, int B, int D, int H, int W, int flags, cudaStream_t st);   // warp_c8.cu
+
 static int check_dims(int B, int C, int D, int H, int W)
 {
     MVS_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "extents must be positive");
@@ -273,6 +276,8 @@ extern "C" int mvs_warp_taps(const float *rot, const float *trans, const float *
     if (B == 0 || D == 0 || H == 0 || W == 0) return MVS_OK;
     if (int e = check_dims(B, 1, D, H, W)) return e;
     MVS_REQUIRE(rot && trans && depth && x0 && y0 && mask, "null pointer");
+    if (flags & MVS_FAST_COORDS)
+        return warp_taps_fast(rot, trans, depth, depth_mode, x0, y0, mask, ixy, B, D, H, W, flags, (cudaStream_t)stream);
     dim3 grid(cdiv(W, 32), cdiv(H, 8), B * D), block(32, 8);
     warp_taps_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(rot, trans, depth, depth_mode, x0, y0, mask, ixy, B, D,
                                                                H, W, make_geom(H, W, flags));

@@ -390,3 +390,45 @@ def test_full_size_properties(C, D, H, W):
     fast = ops.unpack_c8(ops.cost_volume_c8(ops.pack_c8(fb[0]), [ops.pack_c8(t) for t in fb[1:]], rots, trs, depth), C)
     err = (fast - strict).abs()
     assert (err <= strict.abs() * 2 ** -7 + 2e-3).all()
+
+
+# ---- fast-path tap arithmetic (C8 builder): indices must still be the reference's -------------------
+@pytest.mark.parametrize("shape", [(1, 48, 128, 160), (1, 8, 296, 400), (2, 3, 37, 50), (1, 2, 5, 33)])
+@pytest.mark.parametrize("pixel", [False, True])
+@pytest.mark.parametrize("flags", [0, 3])
+def test_fast_path_tap_indices_bitexact(shape, pixel, flags):
+    """The C8 builder replaces the IEEE-division calls by the reciprocal/Newton/residual sequence;
+    its sample positions, integer taps and masks must stay bit-identical to the oracle."""
+    from mvs_b200 import ops, _lib as L
+    B, D, H, W = shape
+    proj = cases.synth.proj_matrices(2, W, seed=5, batch=B)
+    p = torch.from_numpy(proj)
+    prod = (p[:, 1] @ torch.inverse(p[:, 0])).numpy()
+    rot, tr = rt(prod)
+    depth = cases.synth.depth_per_pixel(D, H, W, 10.6, B) if pixel else cases.synth.depth_planes(D, B)
+    x0, y0, mask, ixy = ops.warp_taps(cu(rot.reshape(-1, 9)), cu(tr), cu(depth), H, W, flags | L.FAST_COORDS)
+    ox0, oy0, omask, oixy = O.warp_taps(rot, tr, depth, H, W, flags)
+    assert_bitexact(npy(ixy), oixy)
+    assert np.array_equal(npy(x0), ox0) and np.array_equal(npy(y0), oy0)
+    assert np.array_equal(npy(mask), omask)
+
+
+@pytest.mark.parametrize("C,pixel,nsrc", [(32, False, 4), (8, True, 2)])
+def test_cost_volume_c8_bf16_blend_vs_oracle(C, pixel, nsrc):
+    """MVS_BLEND_BF16: the bilinear blend itself runs in packed bf16 (weights and partial sums rounded
+    to 8 mantissa bits), sums over views in fp32.  Stated tolerance vs the fp32 oracle on the same
+    bf16 features: 2^-5 relative + 0.03 absolute (features ~N(0,1))."""
+    from mvs_b200 import ops, _lib as L
+    v = cases.volume_case(n_views=nsrc + 1, C=C, H=21, W=40, D=6, seed=30 + C, per_pixel=pixel)
+    feats = torch.from_numpy(v["feats"]).bfloat16().float().numpy()
+    p = torch.from_numpy(v["proj"])
+    prod = torch.stack([p[:, i] @ torch.inverse(p[:, 0]) for i in range(1, nsrc + 1)], 1).numpy()
+    rot, tr = rt(prod)
+    ref = O.cost_volume(feats[0], feats[1:], rot, tr, v["depth"])
+    rots = [cu(rot[:, i].reshape(-1, 9)) for i in range(nsrc)]
+    trs = [cu(tr[:, i]) for i in range(nsrc)]
+    packed = [ops.pack_c8(cu(f)) for f in feats]
+    vol = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, cu(v["depth"]), L.BLEND_BF16)
+    out = npy(ops.unpack_c8(vol, C))
+    np.testing.assert_allclose(out, ref, rtol=2 ** -5, atol=3e-2)
+    print("bf16-blend max abs err", np.abs(out - ref).max(), "mean abs err", np.abs(out - ref).mean())

@@ -52,11 +52,12 @@ def main():
         _, _, mask, _ = ops.warp_taps(rots[0], trs[0], depth, h, w, want_ixy=False)
         inb = float((mask == 15).float().mean())
         del mask
-        modes = ["c8", "strict"] if a.mode == "both" else [a.mode]
+        modes = ["c8", "c8b", "strict"] if a.mode == "both" else a.mode.split(",")
         for mode in modes:
-            if mode == "c8":
+            if mode in ("c8", "c8b"):
                 packed = [ops.pack_c8(f) for f in feats]
-                fn = lambda: ops.cost_volume_c8(packed[0], packed[1:], rots, trs, depth)
+                fl = 64 if mode == "c8b" else 0        # MVS_BLEND_BF16
+                fn = lambda: ops.cost_volume_c8(packed[0], packed[1:], rots, trs, depth, fl)
                 s = 2
             else:
                 fn = lambda: ops.cost_volume(feats[0], feats[1:], rots, trs, depth)
