@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .modules import DepthNet, build_cost_volume, regress
+from .modules import stage_forward, cas_relative_poses
 from . import _lib as L
 
 STAGE_SCALES = {"stage1": 4, "stage2": 2, "stage3": 1}   # CasMVSNet/models/cas_mvsnet.py:86-96
@@ -37,7 +37,9 @@ def cascade_hot_path(features: Sequence[Dict[str, torch.Tensor]], proj_matrices:
         depth_min = float(depth_values[0, 0].cpu().numpy())     # the reference's D2H sync, cas_mvsnet.py:110-111
         depth_max = float(depth_values[0, -1].cpu().numpy())
     depth_interval = (depth_max - depth_min) / depth_values.size(1)
-    net = DepthNet()
+    # relative poses of all stages and views in one batched pass (a handful of launches instead of ~50 per stage)
+    keys = ["stage%d" % (i + 1) for i in range(len(ndepths))]
+    rot_all, trans_all = cas_relative_poses(torch.stack([proj_matrices[k] for k in keys], 0))   # [S,B,N-1,9|3]
     outputs = {}
     depth = None
     for stage_idx, nd in enumerate(ndepths):
@@ -64,7 +66,8 @@ def cascade_hot_path(features: Sequence[Dict[str, torch.Tensor]], proj_matrices:
                                 align_corners=False).squeeze(1)
         reg = cost_regularization if not isinstance(cost_regularization, (list, tuple, torch.nn.ModuleList)) \
             else cost_regularization[stage_idx]
-        out = net(feats, proj_matrices[key], hyp, nd, reg)
+        assert len(feats) == proj_matrices[key].shape[1], "Different number of images and projection matrices"
+        out = stage_forward(feats, rot_all[stage_idx], trans_all[stage_idx], hyp, reg, clamp_index=True)
         depth = out["depth"]
         outputs[key] = out
         outputs.update(out)

@@ -267,6 +267,41 @@ def build_cost_volume_c8(ref_fea, src_feas: Sequence[torch.Tensor], ref_proj, sr
                               flags)
 
 
+def stage_forward(features, rot, trans, depth_values, cost_regularization, clamp_index=True, flags=0,
+                  prob_volume_init=None):
+    """One cascade stage from pre-computed relative poses (rot [B,nsrc,9], trans [B,nsrc,3]):
+    fused builder -> CostRegNet -> softmax/regression/confidence.  Used by the multi-stage drivers,
+    which batch the 4x4 pose algebra of all views and stages into a handful of launches."""
+    nsrc = len(features) - 1
+    rots = [rot[:, i].contiguous() for i in range(nsrc)]
+    transs = [trans[:, i].contiguous() for i in range(nsrc)]
+    if _is_fast(cost_regularization):
+        as_c8 = lambda t: t if (t.dim() == 5 and t.dtype == torch.bfloat16 and t.shape[-1] == 8) else ops.pack_c8(t)
+        var = ops.cost_volume_c8(as_c8(features[0]), [as_c8(f) for f in features[1:]], rots, transs, depth_values, flags)
+    else:
+        var = ops.cost_volume(features[0], list(features[1:]), rots, transs, depth_values, flags)
+    cost_reg = cost_regularization(var)
+    logits = cost_reg.squeeze(1) if cost_reg.dim() == 5 else cost_reg
+    if prob_volume_init is not None:
+        logits = logits + prob_volume_init
+    depth, conf = regress(logits, depth_values, clamp_index=clamp_index)
+    return {"depth": depth, "photometric_confidence": conf}
+
+
+def cas_relative_poses(proj_matrices):
+    """[..., N, 2, 4, 4] CasMVSNet projection blocks -> rot [..., N-1, 9], trans [..., N-1, 3] of every
+    source view relative to view 0: K[:3,:3] @ E[:3,:4] (cas_mvsnet.py:30-33), src @ inverse(ref)
+    (module.py:257-259), batched over all leading dimensions."""
+    with torch.no_grad():
+        fused = proj_matrices[..., 0, :, :].clone()
+        fused[..., :3, :4] = torch.matmul(proj_matrices[..., 1, :3, :3], proj_matrices[..., 0, :3, :4])
+        ref_inv = torch.inverse(fused[..., 0, :, :])
+        prod = torch.matmul(fused[..., 1:, :, :], ref_inv.unsqueeze(-3))
+        rot = prod[..., :3, :3].reshape(*prod.shape[:-2], 9).float().contiguous()
+        trans = prod[..., :3, 3].float().contiguous()
+    return rot, trans
+
+
 def _is_fast(cost_regularization) -> bool:
     return getattr(cost_regularization, "mode", "strict") == "fast"
 
