@@ -195,9 +195,29 @@ def main_ours(args):
             return cascade.cascade_hot_path(fs, projs, dv, regs, ndepths=NDEPTHS, img_hw=IMG_HW, depth_min=dmin,
                                             depth_max=dmax)
 
+    # e2e: every step copies ITS inputs from pinned host memory and reads its result back.  The copy of
+    # step i+1 runs on a copy stream into the other half of a double buffer while step i computes --
+    # how a feeder thread would drive the C-ABI; nothing is reused across steps.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dbuf = [[{k: torch.empty_like(t, device=dev) for k, t in f.items()} for f in pinned] for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    e2e_i = [0]
+
     def step_e2e():
-        fs = [{k: t.to(dev, non_blocking=True) for k, t in f.items()} for f in pinned]
-        out = step(fs)
+        i = e2e_i[0]; e2e_i[0] += 1
+        j = i % 2
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            if i >= 2:
+                copy_stream.wait_event(ev_free[j])       # the step that last read this buffer has finished
+            for fd, fh in zip(dbuf[j], pinned):
+                for k, t in fh.items():
+                    fd[k].copy_(t, non_blocking=True)
+            ev_ready[j].record(copy_stream)
+        cur.wait_event(ev_ready[j])
+        out = step(dbuf[j])
+        ev_free[j].record(cur)
         host_out[0].copy_(out["depth"], non_blocking=True)
         host_out[1].copy_(out["photometric_confidence"], non_blocking=True)
 

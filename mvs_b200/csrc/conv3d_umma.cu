@@ -113,6 +113,17 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t a_desc, u
         :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
 }
 
+// Same, but predicated on `issue` INSIDE the PTX: no C++ branch around the instruction, so the compiler
+// emits no BSSY/BSYNC reconvergence pair per MMA in the (warp-uniform) issue loop.
+__device__ __forceinline__ void umma_bf16_ss_if(uint32_t issue, uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue));
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
@@ -198,7 +209,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     uint64_t *tempty = tfull + 2;                // [2]     accumulators drained    (128 epilogue arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch, issuer id)
     const int m0 = blockIdx.x * 128;
     const int h0 = blockIdx.y * P.ht;
     const int b = blockIdx.z / P.cout_tiles, ct = blockIdx.z % P.cout_tiles;
@@ -298,18 +310,17 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 const int buf = step & 1, use = step >> 1;
                 if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
                 tc_fence_after();
-                const uint32_t s0 = sa_units + (uint32_t)(((first + 0) % P.ring) * P.slab_units);
-                const uint32_t s1 = sa_units + (uint32_t)(((first + 1) % P.ring) * P.slab_units);
-                const uint32_t s2 = sa_units + (uint32_t)(((first + 2) % P.ring) * P.slab_units);
+                const int slot0 = first % P.ring;
                 const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
 #pragma unroll 4
                 for (int i = op0; i < op1; ++i) {
                     const uint4 e = P.ops[i];
-                    const uint32_t rd = e.w & 3u;
-                    const uint32_t base = rd == 0 ? s0 : (rd == 1 ? s1 : s2);
+                    int slot = slot0 + (int)(e.w & 3u);
+                    slot -= slot >= P.ring ? P.ring : 0;
+                    const uint32_t base = sa_units + (uint32_t)(slot * P.slab_units);
                     const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e.x + base) & 0x3FFF3FFFu);
                     const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)((e.y + sw_units) & 0x3FFF3FFFu);
-                    if (leader) umma_bf16_ss(tbase + e.z, ad, bd, idesc, (e.w & 0x80u) ? 0u : 1u);
+                    umma_bf16_ss_if(leader, tbase + e.z, ad, bd, idesc, (e.w & 0x80u) ? 0u : 1u);
                 }
                 if (leader) {
                     // slabs the next step no longer reads go back to the producers once these MMAs retire

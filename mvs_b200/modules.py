@@ -295,7 +295,7 @@ def cas_relative_poses(proj_matrices):
     with torch.no_grad():
         fused = proj_matrices[..., 0, :, :].clone()
         fused[..., :3, :4] = torch.matmul(proj_matrices[..., 1, :3, :3], proj_matrices[..., 0, :3, :4])
-        ref_inv = torch.inverse(fused[..., 0, :, :])
+        ref_inv = torch.linalg.inv_ex(fused[..., 0, :, :]).inverse   # == torch.inverse without its device->host "singular?" sync
         prod = torch.matmul(fused[..., 1:, :, :], ref_inv.unsqueeze(-3))
         rot = prod[..., :3, :3].reshape(*prod.shape[:-2], 9).float().contiguous()
         trans = prod[..., :3, 3].float().contiguous()

@@ -83,7 +83,7 @@ def relative_pose(src_proj: torch.Tensor, ref_proj: torch.Tensor, ref_is_inverse
     """proj = src_proj @ inverse(ref_proj) -> (rot [B,9], trans [B,3]) fp32 contiguous.
     Same two torch ops as the reference (MVSNet/models/module.py:63-65)."""
     with torch.no_grad():
-        proj = torch.matmul(src_proj, ref_proj if ref_is_inverse else torch.inverse(ref_proj))
+        proj = torch.matmul(src_proj, ref_proj if ref_is_inverse else torch.linalg.inv_ex(ref_proj).inverse)   # torch.inverse minus its D2H singularity check
         rot = proj[:, :3, :3].reshape(-1, 9).float().contiguous()
         trans = proj[:, :3, 3].float().contiguous()
     return rot, trans
