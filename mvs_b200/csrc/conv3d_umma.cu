@@ -312,15 +312,33 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 tc_fence_after();
                 const int slot0 = first % P.ring;
                 const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
-#pragma unroll 4
-                for (int i = op0; i < op1; ++i) {
-                    const uint4 e = P.ops[i];
+                // four ops per reconvergence region: descriptors for the group are built by the whole warp in
+                // the uniform datapath, then ONE elected lane issues the four MMAs
+                auto desc_of = [&](const uint4 &e, uint64_t &ad, uint64_t &bd, uint32_t &dcol, uint32_t &acc) {
                     int slot = slot0 + (int)(e.w & 3u);
                     slot -= slot >= P.ring ? P.ring : 0;
                     const uint32_t base = sa_units + (uint32_t)(slot * P.slab_units);
-                    const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e.x + base) & 0x3FFF3FFFu);
-                    const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)((e.y + sw_units) & 0x3FFF3FFFu);
-                    umma_bf16_ss_if(leader, tbase + e.z, ad, bd, idesc, (e.w & 0x80u) ? 0u : 1u);
+                    ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e.x + base) & 0x3FFF3FFFu);
+                    bd = ((uint64_t)kDescHi << 32) | (uint64_t)((e.y + sw_units) & 0x3FFF3FFFu);
+                    dcol = tbase + e.z;
+                    acc = (e.w & 0x80u) ? 0u : 1u;
+                };
+                int i = op0;
+                for (; i + 4 <= op1; i += 4) {
+                    uint64_t ad[4], bd[4];
+                    uint32_t dc[4], ac[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) desc_of(P.ops[i + j], ad[j], bd[j], dc[j], ac[j]);
+                    if (leader) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) umma_bf16_ss(dc[j], ad[j], bd[j], idesc, ac[j]);
+                    }
+                }
+                for (; i < op1; ++i) {
+                    uint64_t ad, bd;
+                    uint32_t dc, ac;
+                    desc_of(P.ops[i], ad, bd, dc, ac);
+                    if (leader) umma_bf16_ss(dc, ad, bd, idesc, ac);
                 }
                 if (leader) {
                     // slabs the next step no longer reads go back to the producers once these MMAs retire
