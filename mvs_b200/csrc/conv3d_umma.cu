@@ -70,7 +70,8 @@ struct ConvPlan {
     int od_mul, oh_mul, w_mul;
     int n_ops, n_acc, steps;
     int relu, out_f32, has_skip;
-    int n_issuers, op_begin[UM_MAX_ISSUERS + 1];   // issuer warp j owns ops [op_begin[j], op_begin[j+1])
+    int n_issuers;
+    int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
     //   x = a_off | a_lbo << 16      (+ slab base at issue time)      y = b_off | N << 16   (+ weights base)
@@ -208,6 +209,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     uint64_t *tfull = bars + 2 * UM_MAX_RING;    // [2]     accumulators complete   (1 tcgen05.commit)
     uint64_t *tempty = tfull + 2;                // [2]     accumulators drained    (128 epilogue arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    float *s_scale = reinterpret_cast<float *>(tmem_slot + 4);       // [n] folded-BN scale of this Cout tile (0 for padding)
+    float *s_shift = s_scale + 32;                                   // [n] shift
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch, issuer id)
@@ -224,6 +227,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     {   // weights: staged once per CTA
         const uint4 *src = wpk + (size_t)ct * P.weight_units;
         for (int i = tid; i < P.weight_units; i += UM_THREADS) sw[i] = __ldg(src + i);
+    }
+    if (tid < P.n) {   // epilogue affine of this Cout tile; padded channels get (0, 0) so they store 0
+        const int c = ct * P.n + tid;
+        s_scale[tid] = c < P.cout ? (scale ? __ldg(scale + c) : 1.f) : 0.f;
+        s_shift[tid] = c < P.cout ? (shift ? __ldg(shift + c) : 0.f) : 0.f;
     }
     fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
@@ -299,7 +307,6 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
             const uint32_t idesc = umma_idesc_bf16(128, P.n);
             constexpr uint32_t kDescHi = 8u | (1u << 14);           // SBO = 8 units (128 B) | version = 1 (bit 46)
-            const int op0 = P.op_begin[iss], op1 = P.op_begin[iss + 1];
             int waited = 0;
             for (int step = 0; step < P.steps; ++step) {
                 const int first = P.d_mul * step;
@@ -310,35 +317,35 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 const int buf = step & 1, use = step >> 1;
                 if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
                 tc_fence_after();
-                const int slot0 = first % P.ring;
                 const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
-                // four ops per reconvergence region: descriptors for the group are built by the whole warp in
-                // the uniform datapath, then ONE elected lane issues the four MMAs
-                auto desc_of = [&](const uint4 &e, uint64_t &ad, uint64_t &bd, uint32_t &dcol, uint32_t &acc) {
-                    int slot = slot0 + (int)(e.w & 3u);
-                    slot -= slot >= P.ring ? P.ring : 0;
-                    const uint32_t base = sa_units + (uint32_t)(slot * P.slab_units);
-                    ad = ((uint64_t)kDescHi << 32) | (uint64_t)((e.x + base) & 0x3FFF3FFFu);
-                    bd = ((uint64_t)kDescHi << 32) | (uint64_t)((e.y + sw_units) & 0x3FFF3FFFu);
-                    dcol = tbase + e.z;
-                    acc = (e.w & 0x80u) ? 0u : 1u;
-                };
-                int i = op0;
-                for (; i + 4 <= op1; i += 4) {
-                    uint64_t ad[4], bd[4];
-                    uint32_t dc[4], ac[4];
+                // ops are grouped by the depth slab they read, so the slab base is loop-invariant and an op
+                // costs one 16 B constant load + three adds + the predicate in the uniform datapath
+                for (int r = 0; r < P.rd; ++r) {
+                    const uint32_t base = sa_units + (uint32_t)(((first + r) % P.ring) * P.slab_units);
+                    const int op0 = P.op_begin[iss][r], op1 = P.op_begin[iss][r + 1];
+                    int i = op0;
+                    for (; i + 4 <= op1; i += 4) {
+                        uint64_t ad[4], bd[4];
+                        uint32_t dc[4], ac[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) desc_of(P.ops[i + j], ad[j], bd[j], dc[j], ac[j]);
-                    if (leader) {
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 e = P.ops[i + j];
+                            ad[j] = ((uint64_t)kDescHi << 32) | (uint64_t)(e.x + base);
+                            bd[j] = ((uint64_t)kDescHi << 32) | (uint64_t)(e.y + sw_units);
+                            dc[j] = tbase + e.z;
+                            ac[j] = e.w;
+                        }
+                        if (leader) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) umma_bf16_ss(dc[j], ad[j], bd[j], idesc, ac[j]);
+                            for (int j = 0; j < 4; ++j) umma_bf16_ss(dc[j], ad[j], bd[j], idesc, ac[j]);
+                        }
                     }
-                }
-                for (; i < op1; ++i) {
-                    uint64_t ad, bd;
-                    uint32_t dc, ac;
-                    desc_of(P.ops[i], ad, bd, dc, ac);
-                    if (leader) umma_bf16_ss(dc, ad, bd, idesc, ac);
+                    for (; i < op1; ++i) {
+                        const uint4 e = P.ops[i];
+                        const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)(e.x + base);
+                        const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(e.y + sw_units);
+                        if (leader) umma_bf16_ss(tbase + e.z, ad, bd, idesc, e.w);
+                    }
                 }
                 if (leader) {
                     // slabs the next step no longer reads go back to the producers once these MMAs retire
@@ -368,7 +375,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     const int c0 = ct * P.n + n0;
                     if (!ok || c0 >= P.cout) continue;
                     if (P.out_f32) {
-                        float o = v[0] * (scale ? __ldg(scale) : 1.f) + (shift ? __ldg(shift) : 0.f);
+                        float o = fmaf(v[0], s_scale[0], s_shift[0]);
                         if (P.relu) o = fmaxf(o, 0.f);
                         reinterpret_cast<float *>(y)[(((size_t)b * P.Do + od) * P.Ho + oh) * P.Wo + ow] = o;
                         continue;
@@ -378,14 +385,16 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         const int cc = c0 + half * 8;
                         if (cc >= P.cout_chunks * 8) break;
                         float o[8];
+                        const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + n0 + half * 8);
+                        const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + n0 + half * 8);
+                        const float4 sa = sc4[0], sb = sc4[1], ha = sh4[0], hb = sh4[1];
+                        const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                        const float shv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const int c = cc + e;
-                            const float sc = (scale && c < P.cout) ? __ldg(scale + c) : 1.f;
-                            const float sh = (shift && c < P.cout) ? __ldg(shift + c) : 0.f;
-                            float t = fmaf(v[half * 8 + e], sc, sh);
+                            float t = fmaf(v[half * 8 + e], scv[e], shv[e]);
                             if (P.relu) t = fmaxf(t, 0.f);
-                            o[e] = c < P.cout ? t : 0.f;
+                            o[e] = t;
                         }
                         const size_t oidx = ((((size_t)b * P.cout_chunks + (cc >> 3)) * P.Do + od) * P.Ho + oh) * P.Wo + ow;
                         if (P.has_skip) {
@@ -516,7 +525,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
 
 static size_t plan_smem_bytes(int weight_units, int ring, int slab_units)
 {
-    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16;
+    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16 + 64 * 4;
 }
 
 static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
@@ -600,26 +609,40 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             ao.wadd = deconv ? (int8_t)(c & 1) : 0;
         }
     }
-    // issuer j owns accumulators {a : a % n_issuers == j}; its ops are contiguous in the table
+    // issuer j owns accumulators {a : a % n_issuers == j}; within an issuer the ops are grouped by the
+    // depth slab they read (rd), round-robin over its accumulators inside a group.  The first op an
+    // accumulator sees in that order overwrites it (e.w = 0), all later ones accumulate (e.w = 1).
     P.n_issuers = P.n_acc < UM_MAX_ISSUERS ? P.n_acc : UM_MAX_ISSUERS;
     int n_ops = 0;
-    for (int iss = 0; iss < P.n_issuers; ++iss) {
-        P.op_begin[iss] = n_ops;
-        for (size_t j = 0;; ++j) {
-            bool any = false;
+    std::vector<char> started((size_t)P.n_acc, 0);
+    for (int iss = 0; iss < UM_MAX_ISSUERS; ++iss) {
+        for (int r = 0; r < 3; ++r) {
+            P.op_begin[iss][r] = n_ops;
+            if (iss >= P.n_issuers) continue;
+            std::vector<std::vector<MmaOp>> sel;
             for (int a = iss; a < P.n_acc; a += P.n_issuers) {
-                const std::vector<MmaOp> &v = per_acc[(size_t)a];
-                if (j >= v.size()) continue;
-                const MmaOp &op = v[j];
-                P.ops[n_ops++] = make_uint4((uint32_t)op.a_off | ((uint32_t)op.a_lbo << 16),
-                                            (uint32_t)op.b_off | ((uint32_t)g.n << 16), (uint32_t)op.acc * (uint32_t)g.n,
-                                            (uint32_t)op.rd_first);
-                any = true;
+                std::vector<MmaOp> v;
+                for (const MmaOp &op : per_acc[(size_t)a]) if ((op.rd_first & 3) == r) v.push_back(op);
+                sel.push_back(v);
             }
-            if (!any) break;
+            for (size_t j = 0;; ++j) {
+                bool any = false;
+                for (const auto &v : sel) {
+                    if (j >= v.size()) continue;
+                    const MmaOp &op = v[j];
+                    const uint32_t accumulate = started[op.acc] ? 1u : 0u;
+                    started[op.acc] = 1;
+                    // low 14 bits + smem base stay below 2^14 (227 KB / 16), so no masking at issue time
+                    P.ops[n_ops++] = make_uint4((uint32_t)op.a_off | ((uint32_t)op.a_lbo << 16),
+                                                (uint32_t)op.b_off | ((uint32_t)g.n << 16), (uint32_t)op.acc * (uint32_t)g.n,
+                                                accumulate);
+                    any = true;
+                }
+                if (!any) break;
+            }
         }
+        P.op_begin[iss][3] = n_ops;
     }
-    for (int iss = P.n_issuers; iss <= UM_MAX_ISSUERS; ++iss) P.op_begin[iss] = n_ops;
     P.n_ops = n_ops;
     return true;
 }
