@@ -188,6 +188,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// TMEM loads WITHOUT the wait: issue several, then tmem_wait_ld() once.
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld1_nowait(uint32_t taddr, uint32_t &r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -363,53 +384,95 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const int buf = step & 1, use = step >> 1;
             mbar_wait(tfull + buf, (uint32_t)use & 1u);
             tc_fence_after();
-            for (int a = 0; a < P.n_acc; ++a) {
+            const size_t vol_o = (size_t)P.Do * P.Ho * P.Wo;
+            const uint32_t tcol0 = lane_base + (uint32_t)(buf * P.acc_cols);
+            // affine + ReLU + skip + store of one 8-channel block held in v[0..7]
+            auto store_chunk = [&](const uint32_t (&v)[8], int nloc, size_t oidx) {
+                const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + nloc);
+                const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + nloc);
+                const float4 sa = sc4[0], sb = sc4[1], ha = sh4[0], hb = sh4[1];
+                const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const float shv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float t = fmaf(__uint_as_float(v[e]), scv[e], shv[e]);
+                    if (P.relu) t = fmaxf(t, 0.f);
+                    o[e] = t;
+                }
+                if (P.has_skip) {
+                    const uint4 sk = __ldg(skip + oidx);
+                    const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        o[2 * e] += __uint_as_float(sv[e] << 16);
+                        o[2 * e + 1] += __uint_as_float(sv[e] & 0xffff0000u);
+                    }
+                }
+                uint4 pk;
+                pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+                pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+                reinterpret_cast<uint4 *>(y)[oidx] = pk;
+            };
+            auto out_pos = [&](int a, bool &ok) -> size_t {      // voxel index of accumulator a's row for this thread
                 const AccOut ao = P.acc[a];
                 const int od = P.od_mul * step + ao.dd;
                 const int oh = P.oh_mul * (h0 + ao.th) + ao.dh;
                 const int ow = P.w_mul * (m0 + m) + ao.wadd;
-                const bool ok = od < P.Do && oh < P.Ho && ow < P.Wo;
-                for (int n0 = 0; n0 < P.n; n0 += 16) {
-                    float v[16];
-                    tmem_ld16(lane_base + (uint32_t)(buf * P.acc_cols + a * P.n + n0), v);
-                    const int c0 = ct * P.n + n0;
-                    if (!ok || c0 >= P.cout) continue;
-                    if (P.out_f32) {
-                        float o = fmaf(v[0], s_scale[0], s_shift[0]);
+                ok = od < P.Do && oh < P.Ho && ow < P.Wo;
+                return ((size_t)od * P.Ho + oh) * P.Wo + ow;
+            };
+            if (P.out_f32) {
+                // `prob` layer: one real channel -> fp32 logits; four rows' single-column loads per wait
+                for (int a0 = 0; a0 < P.n_acc; a0 += 4) {
+                    uint32_t r[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (a0 + j < P.n_acc) tmem_ld1_nowait(tcol0 + (uint32_t)((a0 + j) * P.n), r[j]);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (a0 + j >= P.n_acc) break;
+                        bool ok;
+                        const size_t pos = out_pos(a0 + j, ok);
+                        if (!ok) continue;
+                        float o = fmaf(__uint_as_float(r[j]), s_scale[0], s_shift[0]);
                         if (P.relu) o = fmaxf(o, 0.f);
-                        reinterpret_cast<float *>(y)[(((size_t)b * P.Do + od) * P.Ho + oh) * P.Wo + ow] = o;
-                        continue;
+                        reinterpret_cast<float *>(y)[(size_t)b * vol_o + pos] = o;
                     }
+                }
+            } else if (P.cout <= 8) {
+                // one 8-channel block per row: x8 loads, two rows in flight per wait
+                for (int a0 = 0; a0 < P.n_acc; a0 += 2) {
+                    uint32_t r0[8], r1[8];
+                    tmem_ld8_nowait(tcol0 + (uint32_t)(a0 * P.n), r0);
+                    const bool two = a0 + 1 < P.n_acc;
+                    if (two) tmem_ld8_nowait(tcol0 + (uint32_t)((a0 + 1) * P.n), r1);
+                    tmem_wait_ld();
+                    bool ok;
+                    size_t pos = out_pos(a0, ok);
+                    if (ok) store_chunk(r0, 0, (size_t)b * P.cout_chunks * vol_o + pos);
+                    if (two) {
+                        pos = out_pos(a0 + 1, ok);
+                        if (ok) store_chunk(r1, 0, (size_t)b * P.cout_chunks * vol_o + pos);
+                    }
+                }
+            } else {
+                for (int a = 0; a < P.n_acc; ++a) {
+                    bool ok;
+                    const size_t pos = out_pos(a, ok);
+                    for (int n0 = 0; n0 < P.n; n0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16_nowait(tcol0 + (uint32_t)(a * P.n + n0), r);
+                        tmem_wait_ld();
+                        const int c0 = ct * P.n + n0;
+                        if (!ok || c0 >= P.cout) continue;
+                        uint32_t lo[8], hi[8];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int cc = c0 + half * 8;
-                        if (cc >= P.cout_chunks * 8) break;
-                        float o[8];
-                        const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + n0 + half * 8);
-                        const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + n0 + half * 8);
-                        const float4 sa = sc4[0], sb = sc4[1], ha = sh4[0], hb = sh4[1];
-                        const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-                        const float shv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float t = fmaf(v[half * 8 + e], scv[e], shv[e]);
-                            if (P.relu) t = fmaxf(t, 0.f);
-                            o[e] = t;
-                        }
-                        const size_t oidx = ((((size_t)b * P.cout_chunks + (cc >> 3)) * P.Do + od) * P.Ho + oh) * P.Wo + ow;
-                        if (P.has_skip) {
-                            const uint4 s = __ldg(skip + oidx);
-                            const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                o[2 * e] += __uint_as_float(sv[e] << 16);
-                                o[2 * e + 1] += __uint_as_float(sv[e] & 0xffff0000u);
-                            }
-                        }
-                        uint4 pk;
-                        pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-                        pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-                        reinterpret_cast<uint4 *>(y)[oidx] = pk;
+                        for (int e = 0; e < 8; ++e) { lo[e] = r[e]; hi[e] = r[8 + e]; }
+                        const size_t base = ((size_t)b * P.cout_chunks + (c0 >> 3)) * vol_o + pos;
+                        store_chunk(lo, n0, base);
+                        if (c0 + 8 < P.cout_chunks * 8) store_chunk(hi, n0 + 8, base + vol_o);
                     }
                 }
             }

@@ -432,3 +432,22 @@ def test_cost_volume_c8_bf16_blend_vs_oracle(C, pixel, nsrc):
     out = npy(ops.unpack_c8(vol, C))
     np.testing.assert_allclose(out, ref, rtol=2 ** -5, atol=3e-2)
     print("bf16-blend max abs err", np.abs(out - ref).max(), "mean abs err", np.abs(out - ref).mean())
+
+
+def test_cvp_pyramid_golden():
+    """CVP-MVSNet network.forward (nscale=2, test mode) from feature pyramids: coarse sweep + one refine
+    level incl. calDepthHypo's statistical interval, vs the reference's outputs."""
+    from mvs_b200 import modules, pyramid
+    g = cases.golden("cvp_network")
+    H, W = 32, 48
+    fine = cases.synth.features(3, 16, H, W, 41, 1)
+    coarse = cases.synth.features(3, 16, H // 2, W // 2, 42, 1)
+    ref_in, src_in, ref_ex, src_ex = cases.synth.cvp_cameras(2, W, 43, 1)
+    reg = _load(modules.CostRegNetCVP(), cases.costreg_state("cvp", seed=15))
+    dmin = torch.tensor([425.0], dtype=torch.float64); dmax = torch.tensor([935.0], dtype=torch.float64)
+    with torch.no_grad():
+        out = pyramid.cvp_hot_path([cu(fine[0]), cu(coarse[0])], [[cu(fine[1]), cu(coarse[1])], [cu(fine[2]), cu(coarse[2])]],
+                                   cu(ref_in), cu(src_in), cu(ref_ex), cu(src_ex), dmin.to(DEV), dmax.to(DEV), reg, (H, W), mode="test")
+    np.testing.assert_allclose(npy(out["depth_est_list"][1]), g["depth1"], rtol=1e-4, atol=0)     # coarse
+    np.testing.assert_allclose(npy(out["depth_est_list"][0]), g["depth0"], rtol=1e-4, atol=0)     # refined
+    np.testing.assert_allclose(npy(out["prob_confidence"]), g["conf"], rtol=2e-3, atol=2e-4)
