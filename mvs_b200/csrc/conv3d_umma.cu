@@ -70,18 +70,18 @@ struct ConvPlan {
     int od_mul, oh_mul, w_mul;
     int n_ops, n_acc, steps;
     int relu, out_f32, has_skip;
-    int n_issuers;
+    int n_issuers, zero_units;                      // zero_units: 16 B units of the all-zero B block (merged mode)
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
     //   x = a_off | a_lbo << 16      (+ slab base at issue time)      y = b_off | N << 16   (+ weights base)
-    //   z = accumulator column (acc * N)                              w = rd (bits 0-1) | first (bit 7)
+    //   z = accumulator column                                        w = accumulate (bit 0) | (MMA N >> 3) << 8
     uint4 ops[UM_MAX_OPS];
 };
 
 struct PackPlan {
-    int cin, cout, n, cout_tiles, n_ksteps, transposed_weights, flip;
-    KStepSrc ks[UM_MAX_KSTEPS];
+    int cin, cout, n, cout_tiles, n_ksteps, nblk, transposed_weights, flip;
+    KStepSrc ks[UM_MAX_KSTEPS];   // [n_ksteps * nblk]: weight source of block `blk` of k-step `k` at [k * nblk + blk]
 };
 
 // ---- device helpers (inline PTX; sm_100a) -----------------------------------------------------------
@@ -223,7 +223,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4 *sw = reinterpret_cast<uint4 *>(smem_raw);                 // packed weights of this Cout tile
-    uint4 *sa = sw + P.weight_units;                                 // ring of depth slabs
+    uint4 *sa = sw + P.weight_units + P.zero_units;                  // ring of depth slabs (after weights + zero block)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sa + (size_t)P.ring * P.slab_units);
     uint64_t *full = bars;                       // [ring]  slab landed            (128 producer arrivals)
     uint64_t *empty = bars + UM_MAX_RING;        // [ring]  slab no longer read     (1 tcgen05.commit)
@@ -248,6 +248,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     {   // weights: staged once per CTA
         const uint4 *src = wpk + (size_t)ct * P.weight_units;
         for (int i = tid; i < P.weight_units; i += UM_THREADS) sw[i] = __ldg(src + i);
+        for (int i = tid; i < P.zero_units; i += UM_THREADS) sw[P.weight_units + i] = make_uint4(0, 0, 0, 0);
     }
     if (tid < P.n) {   // epilogue affine of this Cout tile; padded channels get (0, 0) so they store 0
         const int c = ct * P.n + tid;
@@ -326,7 +327,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             uint32_t leader;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
             const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
-            const uint32_t idesc = umma_idesc_bf16(128, P.n);
+            const uint32_t idesc0 = umma_idesc_bf16(128, 0);        // N comes from the op entry
             constexpr uint32_t kDescHi = 8u | (1u << 14);           // SBO = 8 units (128 B) | version = 1 (bit 46)
             int waited = 0;
             for (int step = 0; step < P.steps; ++step) {
@@ -358,14 +359,15 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         }
                         if (leader) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) umma_bf16_ss(dc[j], ad[j], bd[j], idesc, ac[j]);
+                            for (int j = 0; j < 4; ++j)
+                                umma_bf16_ss(dc[j], ad[j], bd[j], idesc0 | ((ac[j] >> 8) << 17), ac[j] & 1u);
                         }
                     }
                     for (; i < op1; ++i) {
                         const uint4 e = P.ops[i];
                         const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)(e.x + base);
                         const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(e.y + sw_units);
-                        if (leader) umma_bf16_ss(tbase + e.z, ad, bd, idesc, e.w);
+                        if (leader) umma_bf16_ss(tbase + e.z, ad, bd, idesc0 | ((e.w >> 8) << 17), e.w & 1u);
                     }
                 }
                 if (leader) {
@@ -485,23 +487,27 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     if (warp == 0) tmem_dealloc(taddr, (uint32_t)P.tmem_cols);
 }
 
-// Packs fp32 weights into the per-k-step B blocks: [cout_tile][kstep][2 chunks][N rows][8] bf16.
+// Packs fp32 weights into the per-k-step B blocks: [cout_tile][kstep][2 chunks][nblk][N rows][8] bf16
+// (nblk = 3 for kh-merged stride-1 layers: blocks ordered kh = 2, 1, 0; else 1).
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, __nv_bfloat16 *__restrict__ out)
 {
-    const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * P.n * 8;
+    const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * P.nblk * P.n * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int e = (int)(i % 8);
-        const int row = (int)((i / 8) % P.n);
-        const int j = (int)((i / (8LL * P.n)) % 2);
-        const int ks = (int)((i / (16LL * P.n)) % P.n_ksteps);
-        const int ct = (int)(i / (16LL * P.n * P.n_ksteps));
-        const int tap = P.ks[ks].tap[j];
-        const int ci = P.ks[ks].chunk[j] * 8 + e, co = ct * P.n + row;
+        long long t = i;
+        const int e = (int)(t % 8); t /= 8;
+        const int row = (int)(t % P.n); t /= P.n;
+        const int blk = (int)(t % P.nblk); t /= P.nblk;
+        const int j = (int)(t % 2); t /= 2;
+        const int ks = (int)(t % P.n_ksteps);
+        const int ct = (int)(t / P.n_ksteps);
+        const KStepSrc src = P.ks[ks * P.nblk + blk];
+        const int tap = src.tap[j];
+        const int ci = src.chunk[j] * 8 + e, co = ct * P.n + row;
         float v = 0.f;
         if (tap >= 0 && ci < P.cin && co < P.cout) {
-            const int t = P.flip ? 26 - tap : tap;
-            v = P.transposed_weights ? w[((size_t)ci * P.cout + co) * 27 + t] : w[((size_t)co * P.cin + ci) * 27 + t];
+            const int tt = P.flip ? 26 - tap : tap;
+            v = P.transposed_weights ? w[((size_t)ci * P.cout + co) * 27 + tt] : w[((size_t)co * P.cin + ci) * 27 + tt];
         }
         out[i] = __float2bfloat16_rn(v);
     }
@@ -516,7 +522,9 @@ struct KStep {
 
 struct LayerGeom {
     int mode, cin_chunks, n, cout_tiles, arr;
+    int nblk;                            // 3: stride-1 layers merge the three kh taps of an input row into one MMA
     std::vector<KStep> ks;
+    std::vector<KStepSrc> srcs;          // [ks.size() * nblk]
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -537,23 +545,43 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
     auto add = [&](int rd, int rh, int arr, int col, int chunk, int lbo, int cls, int tap0, int ch0, int tap1, int ch1) {
         KStep k{rd, rh, arr, col, chunk, lbo, cls, {{(int8_t)tap0, (int8_t)tap1}, {(int8_t)ch0, (int8_t)ch1}}};
         g.ks.push_back(k);
+        g.srcs.push_back(k.src);
     };
-    if (g.mode == UM_CONV_S1 || g.mode == UM_CONV_S2) {
+    g.nblk = g.mode == UM_CONV_S1 ? 3 : 1;
+    if (g.mode == UM_CONV_S1) {
+        // kh-merged: a k-step is (kd, kw-group, cin pair); its B block holds the kh = 2, 1, 0 taps side by side,
+        // so ONE MMA on input row i feeds output rows i-2 .. i (the A operand is fetched once for three rows)
+        for (int kd = 0; kd < 3; ++kd) {
+            auto tap = [&](int kh, int kw) { return (kd * 3 + kh) * 3 + kw; };
+            auto add3 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1) {
+                KStep k{kd, 0, 0, col, chunk, lbo, 0, {{0, 0}, {0, 0}}};
+                g.ks.push_back(k);
+                for (int kh = 2; kh >= 0; --kh) {
+                    KStepSrc sc{{(int8_t)tap(kh, kw0), (int8_t)(kw1 >= 0 ? tap(kh, kw1) : -1)}, {(int8_t)ch0, (int8_t)ch1}};
+                    g.srcs.push_back(sc);
+                }
+            };
+            if (CH == 1) {
+                add3(0, 0, 1, 0, 0, 1, 0);        // taps kw = 0, 1 on adjacent staged columns (LBO = 16 B)
+                add3(2, 0, 1, 2, 0, -1, 0);       // tap kw = 2 paired with zero weights
+            } else {
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int sidx = 0; sidx < CH; sidx += 2) {
+                        const bool pair = sidx + 1 < CH;
+                        add3(kw, sidx, pair ? plane : 1, kw, sidx, pair ? kw : -1, sidx + 1);
+                    }
+            }
+        }
+    } else if (g.mode == UM_CONV_S2) {
         for (int kd = 0; kd < 3; ++kd)
             for (int kh = 0; kh < 3; ++kh) {
                 auto tap = [&](int kw) { return (kd * 3 + kh) * 3 + kw; };
-                // (array, column shift) of tap kw: stride 1: in[ow-1+kw]; stride 2: kw=0 -> O[c], 1 -> E[c], 2 -> O[c+1]
-                const int arr_of[3] = {g.mode == UM_CONV_S2 ? 1 : 0, 0, g.mode == UM_CONV_S2 ? 1 : 0};
-                const int col_of[3] = {0, g.mode == UM_CONV_S2 ? 0 : 1, g.mode == UM_CONV_S2 ? 1 : 2};
+                // (array, column shift) of tap kw: kw=0 -> O[c], 1 -> E[c], 2 -> O[c+1]
+                const int arr_of[3] = {1, 0, 1};
+                const int col_of[3] = {0, 0, 1};
                 if (CH == 1) {
-                    // Cin = 8: K=16 pairs two taps whose staged columns are adjacent (LBO = 16 B)
-                    if (g.mode == UM_CONV_S1) {
-                        add(kd, kh, 0, 0, 0, 1, 0, tap(0), 0, tap(1), 0);
-                        add(kd, kh, 0, 2, 0, 1, 0, tap(2), 0, -1, 0);
-                    } else {
-                        add(kd, kh, 1, 0, 0, 1, 0, tap(0), 0, tap(2), 0);      // O[c], O[c+1]
-                        add(kd, kh, 0, 0, 0, 1, 0, tap(1), 0, -1, 0);          // E[c], (E[c+1] x 0)
-                    }
+                    add(kd, kh, 1, 0, 0, 1, 0, tap(0), 0, tap(2), 0);      // O[c], O[c+1]
+                    add(kd, kh, 0, 0, 0, 1, 0, tap(1), 0, -1, 0);          // E[c], (E[c+1] x 0)
                 } else {
                     for (int kw = 0; kw < 3; ++kw)
                         for (int s = 0; s < CH; s += 2) {
@@ -598,6 +626,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     memset(&P, 0, sizeof(P));
     P.B = B; P.D = D; P.H = H; P.W = W;
     const bool deconv = g.mode == UM_DECONV_S2;
+    const bool merged = g.nblk == 3;                 // stride-1 conv: kh taps merged along N
     if (deconv) { P.Do = 2 * D; P.Ho = 2 * H; P.Wo = 2 * W; }
     else if (g.mode == UM_CONV_S2) { P.Do = (D - 1) / 2 + 1; P.Ho = (H - 1) / 2 + 1; P.Wo = (W - 1) / 2 + 1; }
     else { P.Do = D; P.Ho = H; P.Wo = W; }
@@ -606,11 +635,11 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip;
     const int S = g.mode == UM_CONV_S2 ? 2 : 1;
     const int acc_per_row = deconv ? 8 : 1;
-    const int ops_per_row = (int)g.ks.size();
-    P.weight_units = (int)g.ks.size() * 2 * g.n;
+    const int packed_units = (int)g.ks.size() * 2 * g.nblk * g.n;     // what mvs_conv3d_c8_pack_weights wrote per Cout tile
     P.rd = deconv ? 2 : 3;
     P.d_mul = deconv ? 1 : S;
     const int rows_h = deconv ? H : P.Ho;
+    auto n_ops_for = [&](int ht) { return merged ? (int)g.ks.size() * (ht + 2) + 1 : (int)g.ks.size() * ht; };
     // ht (rows per CTA) and ring depth: prefer one full step of prefetch and two CTAs per SM, then relax.
     int best = 0, best_ring = 0;
     for (int pass = 0; pass < 3 && !best; ++pass) {
@@ -619,10 +648,11 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         for (int ht = 8; ht >= 1; --ht) {
             if (ht > rows_h && ht > 1) continue;
             // TMEM: two accumulator buffers per CTA; with two CTAs per SM (pass 0) each may take half of the 512 columns
-            if (ht * ops_per_row > UM_MAX_OPS || ht * acc_per_row > UM_MAX_ACC ||
+            if (n_ops_for(ht) > UM_MAX_OPS || ht * acc_per_row > UM_MAX_ACC ||
                 2 * ht * acc_per_row * g.n > (pass == 0 ? 256 : 512)) continue;
             const int rh = deconv ? ht + 1 : S * (ht - 1) + 3;
-            if (plan_smem_bytes(P.weight_units, ring, rh * g.cin_chunks * g.arr * UM_COLS) > budget) continue;
+            const int zero_units = merged ? 2 * ht * g.n : 0;
+            if (plan_smem_bytes(packed_units + zero_units, ring, rh * g.cin_chunks * g.arr * UM_COLS) > budget) continue;
             best = ht; best_ring = ring;
             break;
         }
@@ -632,7 +662,9 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     P.ring = best_ring;
     P.rh = deconv ? P.ht + 1 : S * (P.ht - 1) + 3;
     P.slab_units = P.rh * g.cin_chunks * g.arr * UM_COLS;
-    smem_bytes = plan_smem_bytes(P.weight_units, P.ring, P.slab_units);
+    P.zero_units = merged ? 2 * P.ht * g.n : 0;
+    P.weight_units = packed_units;
+    smem_bytes = plan_smem_bytes(P.weight_units + P.zero_units, P.ring, P.slab_units);
     P.n_acc = P.ht * acc_per_row;
     P.acc_cols = P.n_acc * g.n;
     int cols = 32;
@@ -646,24 +678,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         P.w_base[0] = S == 1 ? -1 : 0; P.w_base[1] = -1;
         P.od_mul = 1; P.oh_mul = 1; P.w_mul = 1; P.steps = P.Do;
     }
-    // ops per accumulator, then emitted round-robin so that consecutive MMAs target different TMEM
-    // accumulators (independent chains pipeline in the tensor core; a single chain serialises)
-    std::vector<std::vector<MmaOp>> per_acc((size_t)P.n_acc);
-    for (int th = 0; th < P.ht; ++th) {
-        for (size_t k = 0; k < g.ks.size(); ++k) {
-            const KStep &ks = g.ks[k];
-            MmaOp op;
-            const int row = S * th + ks.rh;
-            const int a_off = ((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col;
-            const int acc = th * acc_per_row + ks.cls;
-            op.a_off = (uint16_t)a_off;
-            op.b_off = (uint16_t)(k * 2 * g.n);
-            op.a_lbo = (uint16_t)ks.lbo;
-            op.acc = (uint8_t)acc;
-            op.rd_first = (uint8_t)(ks.rd | (per_acc[acc].empty() ? 0x80 : 0));
-            if (ks.lbo > 0x3FFF || a_off > 0xFFFF || k * 2 * g.n > 0xFFFF) return false;
-            per_acc[acc].push_back(op);
-        }
+    for (int th = 0; th < P.ht; ++th)
         for (int c = 0; c < acc_per_row; ++c) {
             AccOut &ao = P.acc[th * acc_per_row + c];
             ao.th = (int8_t)th;
@@ -671,40 +686,89 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             ao.dh = deconv ? (int8_t)((c >> 1) & 1) : 0;
             ao.wadd = deconv ? (int8_t)(c & 1) : 0;
         }
-    }
-    // issuer j owns accumulators {a : a % n_issuers == j}; within an issuer the ops are grouped by the
-    // depth slab they read (rd), round-robin over its accumulators inside a group.  The first op an
-    // accumulator sees in that order overwrites it (e.w = 0), all later ones accumulate (e.w = 1).
-    P.n_issuers = P.n_acc < UM_MAX_ISSUERS ? P.n_acc : UM_MAX_ISSUERS;
+    auto entry = [&](int a_off, int a_lbo, int b_off, int b_lbo, int col, int n_mma, int accumulate) {
+        // low 14 bits + smem base stay below 2^14 (227 KB / 16), so no masking at issue time
+        return make_uint4((uint32_t)a_off | ((uint32_t)a_lbo << 16), (uint32_t)b_off | ((uint32_t)b_lbo << 16), (uint32_t)col,
+                          (uint32_t)accumulate | ((uint32_t)(n_mma >> 3) << 8));
+    };
     int n_ops = 0;
-    std::vector<char> started((size_t)P.n_acc, 0);
-    for (int iss = 0; iss < UM_MAX_ISSUERS; ++iss) {
+    if (merged) {
+        // ONE issuer (the merged MMAs of neighbouring input rows overlap in the accumulators they update).
+        // Step layout: [zero-initialise all ht*n columns] then, per depth slab r = kd and staged input row i,
+        // one MMA per (kw group, cin pair) that updates output rows max(0,i-2) .. min(ht-1,i) with the
+        // kh = i - row taps: B sub-block [2 - (i - lo)] .. of the (kh = 2,1,0)-ordered packed block.
+        P.n_issuers = 1;
+        for (int iss = 0; iss < UM_MAX_ISSUERS; ++iss)
+            for (int r = 0; r < 4; ++r) P.op_begin[iss][r] = 0;
+        if (P.ht * g.n > 256) return false;
+        P.ops[n_ops++] = entry(0, 1, packed_units, P.ht * g.n, 0, P.ht * g.n, 0);   // A: any staged (finite) bytes; B: zeros
+        const int ks_per_kd = (int)g.ks.size() / 3;
         for (int r = 0; r < 3; ++r) {
-            P.op_begin[iss][r] = n_ops;
-            if (iss >= P.n_issuers) continue;
-            std::vector<std::vector<MmaOp>> sel;
-            for (int a = iss; a < P.n_acc; a += P.n_issuers) {
-                std::vector<MmaOp> v;
-                for (const MmaOp &op : per_acc[(size_t)a]) if ((op.rd_first & 3) == r) v.push_back(op);
-                sel.push_back(v);
-            }
-            for (size_t j = 0;; ++j) {
-                bool any = false;
-                for (const auto &v : sel) {
-                    if (j >= v.size()) continue;
-                    const MmaOp &op = v[j];
-                    const uint32_t accumulate = started[op.acc] ? 1u : 0u;
-                    started[op.acc] = 1;
-                    // low 14 bits + smem base stay below 2^14 (227 KB / 16), so no masking at issue time
-                    P.ops[n_ops++] = make_uint4((uint32_t)op.a_off | ((uint32_t)op.a_lbo << 16),
-                                                (uint32_t)op.b_off | ((uint32_t)g.n << 16), (uint32_t)op.acc * (uint32_t)g.n,
-                                                accumulate);
-                    any = true;
+            P.op_begin[0][r] = r == 0 ? 0 : n_ops;
+            for (int i = 0; i < P.rh; ++i) {
+                const int lo = i - 2 < 0 ? 0 : i - 2, hi = i > P.ht - 1 ? P.ht - 1 : i;
+                if (hi < lo) continue;
+                const int cnt = hi - lo + 1, blk0 = 2 - (i - lo);
+                for (int k = r * ks_per_kd; k < (r + 1) * ks_per_kd; ++k) {
+                    const KStep &ks = g.ks[(size_t)k];
+                    const int a_off = ((i * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col;
+                    const int b_off = k * 2 * 3 * g.n + blk0 * g.n;
+                    if (ks.lbo > 0x3FFF || a_off > 0xFFFF || b_off > 0x3FFF) return false;
+                    if (n_ops >= UM_MAX_OPS) return false;
+                    P.ops[n_ops++] = entry(a_off, ks.lbo, b_off, 3 * g.n, lo * g.n, cnt * g.n, 1);
                 }
-                if (!any) break;
             }
         }
-        P.op_begin[iss][3] = n_ops;
+        P.op_begin[0][3] = n_ops;
+        for (int iss = 1; iss < UM_MAX_ISSUERS; ++iss)
+            for (int r = 0; r < 4; ++r) P.op_begin[iss][r] = n_ops;
+    } else {
+        // ops per accumulator; issuer j owns accumulators {a : a % n_issuers == j}; within an issuer the ops
+        // are grouped by the depth slab they read (rd), round-robin over its accumulators inside a group
+        // (independent chains pipeline in the tensor core).  The first op an accumulator sees overwrites it.
+        std::vector<std::vector<MmaOp>> per_acc((size_t)P.n_acc);
+        for (int th = 0; th < P.ht; ++th)
+            for (size_t k = 0; k < g.ks.size(); ++k) {
+                const KStep &ks = g.ks[k];
+                MmaOp op;
+                const int row = S * th + ks.rh;
+                const int a_off = ((row * g.cin_chunks + ks.chunk) * g.arr + ks.arr) * UM_COLS + ks.col;
+                const int acc = th * acc_per_row + ks.cls;
+                op.a_off = (uint16_t)a_off;
+                op.b_off = (uint16_t)(k * 2 * g.n);
+                op.a_lbo = (uint16_t)ks.lbo;
+                op.acc = (uint8_t)acc;
+                op.rd_first = (uint8_t)ks.rd;
+                if (ks.lbo > 0x3FFF || a_off > 0xFFFF || k * 2 * g.n > 0x3FFF) return false;
+                per_acc[(size_t)acc].push_back(op);
+            }
+        P.n_issuers = P.n_acc < UM_MAX_ISSUERS ? P.n_acc : UM_MAX_ISSUERS;
+        std::vector<char> started((size_t)P.n_acc, 0);
+        for (int iss = 0; iss < UM_MAX_ISSUERS; ++iss) {
+            for (int r = 0; r < 3; ++r) {
+                P.op_begin[iss][r] = n_ops;
+                if (iss >= P.n_issuers) continue;
+                std::vector<std::vector<MmaOp>> sel;
+                for (int a = iss; a < P.n_acc; a += P.n_issuers) {
+                    std::vector<MmaOp> v;
+                    for (const MmaOp &op : per_acc[(size_t)a]) if ((op.rd_first & 3) == r) v.push_back(op);
+                    sel.push_back(v);
+                }
+                for (size_t j = 0;; ++j) {
+                    bool any = false;
+                    for (const auto &v : sel) {
+                        if (j >= v.size()) continue;
+                        const MmaOp &op = v[j];
+                        const int accumulate = started[op.acc] ? 1 : 0;
+                        started[op.acc] = 1;
+                        P.ops[n_ops++] = entry(op.a_off, op.a_lbo, op.b_off, g.n, op.acc * g.n, g.n, accumulate);
+                        any = true;
+                    }
+                    if (!any) break;
+                }
+            }
+            P.op_begin[iss][3] = n_ops;
+        }
     }
     P.n_ops = n_ops;
     return true;
@@ -718,7 +782,7 @@ extern "C" int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stri
 {
     if (Cin <= 0 || Cout <= 0 || (stride != 1 && stride != 2)) return -1;
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
-    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * g.n * 16;
+    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * g.nblk * g.n * 16;
 }
 
 extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride, int transposed,
@@ -727,14 +791,14 @@ extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin,
     MVS_REQUIRE(w && packed, "null pointer");
     MVS_REQUIRE(Cin > 0 && Cout > 0 && (stride == 1 || stride == 2), "bad layer shape");
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
-    MVS_REQUIRE((int)g.ks.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
+    MVS_REQUIRE((int)g.srcs.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
     PackPlan pp;
     memset(&pp, 0, sizeof(pp));
-    pp.cin = Cin; pp.cout = Cout; pp.n = g.n; pp.cout_tiles = g.cout_tiles; pp.n_ksteps = (int)g.ks.size();
+    pp.cin = Cin; pp.cout = Cout; pp.n = g.n; pp.cout_tiles = g.cout_tiles; pp.n_ksteps = (int)g.ks.size(); pp.nblk = g.nblk;
     pp.transposed_weights = transposed ? 1 : 0;
     pp.flip = (transposed && stride == 1) ? 1 : 0;       // ConvTranspose3d(stride 1, pad 1) == conv with flipped taps
-    for (size_t k = 0; k < g.ks.size(); ++k) pp.ks[k] = g.ks[k].src;
-    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * g.n * 8;
+    for (size_t k = 0; k < g.srcs.size(); ++k) pp.ks[k] = g.srcs[k];
+    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * g.nblk * g.n * 8;
     pack_weights_kernel<<<cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         pp, w, (__nv_bfloat16 *)packed);
     return check_launch("mvs_conv3d_c8_pack_weights");
@@ -749,7 +813,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     MVS_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
     MVS_REQUIRE(x_c8 && w_packed && y, "null pointer");
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
-    MVS_REQUIRE((int)g.ks.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
+    MVS_REQUIRE((int)g.srcs.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
     static thread_local ConvPlan P;
     size_t smem = 0;
     const bool out_f32 = Cout == 1;
