@@ -71,6 +71,7 @@ struct ConvPlan {
     int n_ops, n_acc, steps;
     int relu, out_f32, has_skip;
     int n_issuers, zero_units;                      // zero_units: 16 B units of the all-zero B block (merged mode)
+    int merged;                                     // stride-1 kh-merged mode: 2 issuers alternate depth steps, epilogue frees slabs
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
@@ -241,8 +242,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     if (tid == 32) {
-        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, UM_PROD_THREADS); mbar_init(empty + i, (uint32_t)P.n_issuers); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, (uint32_t)P.n_issuers); mbar_init(tempty + i, UM_EPI_THREADS); }
+        const uint32_t n_commit = P.merged ? 1u : (uint32_t)P.n_issuers;
+        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, UM_PROD_THREADS); mbar_init(empty + i, n_commit); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, n_commit); mbar_init(tempty + i, UM_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     {   // weights: staged once per CTA
@@ -329,9 +331,16 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
             const uint32_t idesc0 = umma_idesc_bf16(128, 0);        // N comes from the op entry
             constexpr uint32_t kDescHi = 8u | (1u << 14);           // SBO = 8 units (128 B) | version = 1 (bit 46)
+            // merged mode: the issuers alternate depth steps (issuer j owns TMEM buffer j and the whole op
+            // table); otherwise every issuer works on every step with its own slice of accumulators
+            const int step0 = P.merged ? iss : 0, dstep = P.merged ? P.n_issuers : 1;
+            const int tbl = P.merged ? 0 : iss;
             int waited = 0;
-            for (int step = 0; step < P.steps; ++step) {
+            for (int step = step0; step < P.steps; step += dstep) {
                 const int first = P.d_mul * step;
+                // only slabs this step reads: an issuer that skips steps must not test the parity of a
+                // barrier whose slot may already have been released and refilled (the phase would alias)
+                if (waited < first) waited = first;
                 while (waited < first + P.rd) {
                     mbar_wait(full + waited % P.ring, (uint32_t)(waited / P.ring) & 1u);
                     ++waited;
@@ -344,7 +353,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 // costs one 16 B constant load + three adds + the predicate in the uniform datapath
                 for (int r = 0; r < P.rd; ++r) {
                     const uint32_t base = sa_units + (uint32_t)(((first + r) % P.ring) * P.slab_units);
-                    const int op0 = P.op_begin[iss][r], op1 = P.op_begin[iss][r + 1];
+                    const int op0 = P.op_begin[tbl][r], op1 = P.op_begin[tbl][r + 1];
                     int i = op0;
                     for (; i + 4 <= op1; i += 4) {
                         uint64_t ad[4], bd[4];
@@ -372,7 +381,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 }
                 if (leader) {
                     // slabs the next step no longer reads go back to the producers once these MMAs retire
-                    for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + (first + k) % P.ring);
+                    // (merged mode: another issuer's step may still read them -> the epilogue frees them)
+                    if (!P.merged)
+                        for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + (first + k) % P.ring);
                     umma_commit(tfull + buf);
                 }
                 __syncwarp();
@@ -386,6 +397,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const int buf = step & 1, use = step >> 1;
             mbar_wait(tfull + buf, (uint32_t)use & 1u);
             tc_fence_after();
+            if (P.merged && tid == 0) {
+                // steps complete in order as seen from here (we waited on every earlier tfull), so no MMA of
+                // any step <= `step` still reads the slabs this step retires
+                for (int k = 0; k < P.d_mul; ++k) mbar_arrive(empty + (P.d_mul * step + k) % P.ring);
+            }
             const size_t vol_o = (size_t)P.Do * P.Ho * P.Wo;
             const uint32_t tcol0 = lane_base + (uint32_t)(buf * P.acc_cols);
             // affine + ReLU + skip + store of one 8-channel block held in v[0..7]
@@ -697,7 +713,8 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         // Step layout: [zero-initialise all ht*n columns] then, per depth slab r = kd and staged input row i,
         // one MMA per (kw group, cin pair) that updates output rows max(0,i-2) .. min(ht-1,i) with the
         // kh = i - row taps: B sub-block [2 - (i - lo)] .. of the (kh = 2,1,0)-ordered packed block.
-        P.n_issuers = 1;
+        P.merged = 1;
+        P.n_issuers = 2;
         for (int iss = 0; iss < UM_MAX_ISSUERS; ++iss)
             for (int r = 0; r < 4; ++r) P.op_begin[iss][r] = 0;
         if (P.ht * g.n > 256) return false;
