@@ -24,6 +24,7 @@
 //                          (or fp32 logits for the Cout = 1 `prob` layer)
 // The accumulators are double-buffered in TMEM, so step s+1's MMAs overlap step s's epilogue, and
 // the ring holds one step of prefetch, so the loads of step s+1 overlap both.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -658,7 +659,8 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     auto n_ops_for = [&](int ht) { return merged ? (int)g.ks.size() * (ht + 2) + 1 : (int)g.ks.size() * ht; };
     // ht (rows per CTA) and ring depth: prefer one full step of prefetch and two CTAs per SM, then relax.
     int best = 0, best_ring = 0;
-    for (int pass = 0; pass < 3 && !best; ++pass) {
+    static const int first_pass = getenv("MVS_UMMA_FIRST_PASS") ? atoi(getenv("MVS_UMMA_FIRST_PASS")) : 0;   // tuning knob
+    for (int pass = first_pass; pass < 3 && !best; ++pass) {
         const size_t budget = pass == 0 ? 112 * 1024 : 226 * 1024;
         const int ring = pass < 2 ? P.rd + P.d_mul : P.rd;
         for (int ht = 8; ht >= 1; --ht) {
