@@ -156,6 +156,13 @@ int mvs_softargmin_conf_fwd(const float *logits, const float *depth, int depth_m
 int mvs_depth_range_samples(const float *cur, double interval, int ndepth, float *out, int B, int H,
                             int W, void *stream);
 
+/* Fused form of the whole inter-stage step of CascadeMVSNet.forward (cas_mvsnet.py:129-151): bilinear
+ * up-sampling of the previous stage's depth [B,hp,wp] to the image extent [H,W] (align_corners=False),
+ * get_depth_range_samples around it, and trilinear resampling of the [B,D,H,W] samples to the stage
+ * extent [D,h,w] -- written directly as out [B,D,h,w] fp32; the full-resolution volume never exists. */
+int mvs_cas_hypotheses(const float *prev_depth, int hp, int wp, int H, int W, int h, int w, int ndepth,
+                       double interval, float *out, int B, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

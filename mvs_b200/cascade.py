@@ -46,16 +46,21 @@ def cascade_hot_path(features: Sequence[Dict[str, torch.Tensor]], proj_matrices:
         key = "stage%d" % (stage_idx + 1)
         scale = STAGE_SCALES[key]
         feats = [f[key] for f in features]
+        hyp = None
         if depth is not None:
-            cur = F.interpolate(depth.detach().unsqueeze(1), [H, W], mode="bilinear", align_corners=False).squeeze(1)
-            samples = ops.depth_range_samples(cur, nd, depth_interals_ratio[stage_idx] * depth_interval)
+            # bilinear up-sampling + get_depth_range_samples + trilinear resampling (cas_mvsnet.py:129-151), fused
+            hyp = ops.cas_hypotheses(depth.detach(), (H, W), (H // scale, W // scale), nd,
+                                     depth_interals_ratio[stage_idx] * depth_interval)
+            samples = None
         else:
             # first stage: uniform planes between depth_values[:,0] and [:, -1] (module.py:509-517)
             lo, hi = depth_values[:, 0], depth_values[:, -1]
             step = (hi - lo) / (nd - 1)
             planes = lo.unsqueeze(1) + torch.arange(0, nd, device=lo.device, dtype=lo.dtype).reshape(1, -1) * step.unsqueeze(1)
             samples = None
-        if samples is None:
+        if hyp is not None:
+            pass
+        elif samples is None:
             # The reference repeats the planes to [B,D,H,W] at FULL resolution (364 MB at 1600x1184)
             # and trilinearly resamples them to the stage extent (cas_mvsnet.py:150-151); resampling a
             # plane-uniform volume at the same D returns the same constants (probed bitwise, SURVEY.md

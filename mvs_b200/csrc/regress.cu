@@ -68,9 +68,80 @@ depth_range_kernel(const float *__restrict__ cur, float half, int ndepth, float 
         out[((size_t)b * ndepth + k) * plane + i] = __fadd_rn(lo, __fmul_rn((float)k, step));
 }
 
+// ATen's area_pixel_compute_source_index (align_corners = False, non-cubic) + tap set-up of
+// upsample_bilinear2d / upsample_trilinear3d: src = scale * (dst + 0.5) - 0.5, clamped at 0.
+__device__ __forceinline__ void lin_tap(float scale, int dst, int in_size, int &i0, int &i1, float &l0, float &l1)
+{
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.0f - l1;
+}
+
+// Fused hypothesis generation of one cascade stage (CasMVSNet/models/cas_mvsnet.py:129-151,
+// module.py:485-504): bilinear up-sampling of the previous depth to the image extent, +-ndepth/2
+// samples around it, trilinear resampling (D unchanged) to the stage extent -- without
+// materialising the [B,D,H,W] full-resolution sample volume.  Thread <-> output pixel, lanes along x.
+__global__ void __launch_bounds__(256)
+cas_hypotheses_kernel(const float *__restrict__ prev, int hp, int wp, int H, int W, int h, int w, int nd, float half,
+                      float *__restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= w) return;
+    const float *pd = prev + (size_t)b * hp * wp;
+    // trilinear taps of the (H,W) -> (h,w) resampling
+    int Y0, Y1, X0, X1; float ly0, ly1, lx0, lx1;
+    lin_tap((float)H / (float)h, y, H, Y0, Y1, ly0, ly1);
+    lin_tap((float)W / (float)w, x, W, X0, X1, lx0, lx1);
+    // up-sampled previous depth at the (up to) four full-resolution positions
+    float lo[2][2], step[2][2];
+    const float sh = (float)hp / (float)H, sw = (float)wp / (float)W;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int Y = a ? Y1 : Y0, X = c ? X1 : X0;
+            int y0, y1, x0, x1; float my0, my1, mx0, mx1;
+            lin_tap(sh, Y, hp, y0, y1, my0, my1);
+            lin_tap(sw, X, wp, x0, x1, mx0, mx1);
+            const float cur = my0 * (mx0 * __ldg(pd + y0 * wp + x0) + mx1 * __ldg(pd + y0 * wp + x1)) +
+                              my1 * (mx0 * __ldg(pd + y1 * wp + x0) + mx1 * __ldg(pd + y1 * wp + x1));
+            const float l = __fsub_rn(cur, half), hi = __fadd_rn(cur, half);
+            lo[a][c] = l;
+            step[a][c] = __fdiv_rn(__fsub_rn(hi, l), (float)(nd - 1));
+        }
+    const size_t plane = (size_t)h * w;
+    float *op = out + (size_t)b * nd * plane + (size_t)y * w + x;
+    for (int k = 0; k < nd; ++k) {
+        float v[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) v[a][c] = __fadd_rn(lo[a][c], __fmul_rn((float)k, step[a][c]));
+        // depth axis: same extent in and out => tap weight exactly (1, 0) on plane k
+        const float val = ly0 * (lx0 * v[0][0] + lx1 * v[0][1]) + ly1 * (lx0 * v[1][0] + lx1 * v[1][1]);
+        op[(size_t)k * plane] = val;
+    }
+}
+
 }  // namespace mvs
 
 using namespace mvs;
+
+extern "C" int mvs_cas_hypotheses(const float *prev_depth, int hp, int wp, int H, int W, int h, int w, int ndepth,
+                                  double interval, float *out, int B, void *stream)
+{
+    if (B == 0 || h == 0 || w == 0) return MVS_OK;
+    MVS_REQUIRE(B > 0 && B <= 65535 && hp > 0 && wp > 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= 65535, "bad extents");
+    MVS_REQUIRE(ndepth > 1, "ndepth must be > 1");
+    MVS_REQUIRE(prev_depth && out, "null pointer");
+    const float half = (float)((double)ndepth / 2.0 * interval);
+    dim3 grid(cdiv(w, 128), h, B);
+    cas_hypotheses_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(prev_depth, hp, wp, H, W, h, w, ndepth, half, out);
+    return check_launch("mvs_cas_hypotheses");
+}
 
 extern "C" int mvs_softargmin_conf_fwd(const float *logits, const float *depth, int depth_mode, float *out_depth,
                                        float *out_conf, float *out_prob, int32_t *out_index, int B, int D, int H,

@@ -361,6 +361,21 @@ def depth_range_samples(cur_depth, ndepth: int, depth_interval_pixel: float):
     return out
 
 
+def cas_hypotheses(prev_depth, img_hw, stage_hw, ndepth: int, depth_interval_pixel: float):
+    """Fused inter-stage step of CascadeMVSNet.forward (cas_mvsnet.py:129-151): prev_depth [B,hp,wp] ->
+    per-pixel hypotheses [B,ndepth,h,w] at the stage extent (bilinear up-sampling to img_hw, +-ndepth/2
+    samples, trilinear resampling) without the full-resolution intermediate volumes."""
+    prev_depth = _f32c(prev_depth)
+    _dev(prev_depth)
+    B, hp, wp = prev_depth.shape
+    (H, W), (h, w) = img_hw, stage_hw
+    out = torch.empty((B, ndepth, h, w), dtype=torch.float32, device=prev_depth.device)
+    with torch.cuda.device(prev_depth.device):
+        check(lib().mvs_cas_hypotheses(_p(prev_depth), hp, wp, H, W, h, w, ndepth, float(depth_interval_pixel), _p(out),
+                                       B, _stream()), "mvs_cas_hypotheses")
+    return out
+
+
 # ---- fast path: bf16 C8 convolution on the tcgen05 tensor cores -----------------------------------
 def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = False) -> torch.Tensor:
     """fp32 [Cout,Cin,3,3,3] (or [Cin,Cout,3,3,3] when transposed) -> opaque packed bf16 blocks for

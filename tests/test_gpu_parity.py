@@ -451,3 +451,18 @@ def test_cvp_pyramid_golden():
     np.testing.assert_allclose(npy(out["depth_est_list"][1]), g["depth1"], rtol=1e-4, atol=0)     # coarse
     np.testing.assert_allclose(npy(out["depth_est_list"][0]), g["depth0"], rtol=1e-4, atol=0)     # refined
     np.testing.assert_allclose(npy(out["prob_confidence"]), g["conf"], rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("scale,nd", [(2, 32), (1, 8), (4, 6)])
+def test_cas_hypotheses_fused_vs_composition(scale, nd):
+    """The fused inter-stage kernel vs the reference's three-op composition (bilinear up-sampling,
+    get_depth_range_samples, trilinear resampling: cas_mvsnet.py:129-151) run with torch on the GPU."""
+    import torch.nn.functional as F
+    from mvs_b200 import ops
+    H, W = 64, 96
+    prev = cu(np.random.RandomState(3).uniform(450, 900, (2, H // (2 * scale), W // (2 * scale))).astype(np.float32))
+    cur = F.interpolate(prev.unsqueeze(1), [H, W], mode="bilinear", align_corners=False).squeeze(1)
+    samples = ops.depth_range_samples(cur, nd, 2 * 2.65)
+    ref = F.interpolate(samples.unsqueeze(1), [nd, H // scale, W // scale], mode="trilinear", align_corners=False).squeeze(1)
+    out = ops.cas_hypotheses(prev, (H, W), (H // scale, W // scale), nd, 2 * 2.65)
+    np.testing.assert_allclose(npy(out), npy(ref), rtol=3e-7, atol=0)
