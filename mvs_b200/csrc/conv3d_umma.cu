@@ -18,12 +18,25 @@
 // CTA = one M tile of 128 w-positions x ht rows; it owns (batch, h-block, w-block, Cout-tile) and
 // walks the depth axis, so every input byte is fetched (1 + 2/ht) times from L2 and the packed
 // weights are staged once per CTA.  Warp-specialised pipeline, mbarrier-synchronised:
-//   warps 4-7  producers : cp.async (16 B, zero-fill for the halo) input depth-slabs into a ring
-//   warp  8    MMA issuer: one thread walks the op table, tcgen05.mma -> TMEM, tcgen05.commit
-//   warps 0-3  epilogue  : tcgen05.ld (32x32b) -> folded-BN affine + ReLU + skip -> C8 bf16 store
-//                          (or fp32 logits for the Cout = 1 `prob` layer)
-// The accumulators are double-buffered in TMEM, so step s+1's MMAs overlap step s's epilogue, and
-// the ring holds one step of prefetch, so the loads of step s+1 overlap both.
+//   warps 4-7   producers : cp.async (16 B, zero-fill for the halo) input depth-slabs into a ring
+//   warps 8-11  issuers   : walk the op table in the uniform datapath, one elected lane issues
+//                           tcgen05.mma -> TMEM and tcgen05.commit -> mbarrier
+//   warps 0-3   epilogue  : tcgen05.ld (32x32b) -> folded-BN affine + ReLU + skip -> C8 bf16 store
+//                           (or fp32 logits for the Cout = 1 `prob` layer)
+// The accumulators are double-buffered in TMEM (step s+1's MMAs overlap step s's epilogue) and the
+// slab ring holds one step of prefetch.
+//
+// What bounds it (ncu, profiles/): these MMAs are tiny (M128 x N16..48 x K16), so the tensor pipe is
+// limited by operand fetch -- every MMA reads a 4 KB A tile from shared memory -- and by issue rate, not
+// by math.  Hence: (i) stride-1 layers merge the three kh taps of an input row into ONE MMA of
+// N = 3*n whose accumulator columns are the three output rows it feeds (A fetched once for three rows;
+// a zero-B MMA initialises the accumulators; two issuers alternate depth steps so they never share an
+// accumulator, and the epilogue -- which has seen every earlier step complete -- releases the slabs);
+// (ii) the other layers split their accumulators over up to four issuer warps; (iii) op entries are
+// issue-ready 16-byte records in kernel-parameter (constant) space grouped by depth slab, so an MMA
+// costs one uniform load + three adds; descriptors are built by the whole warp on warp-uniform values
+// and only the instruction is predicated on an elected lane (issuing from `if (lane == 0)` makes the
+// compiler wrap every UTCHMMA in an R2UR waterfall loop; predicating inside the PTX is silently dropped).
 #include <cstdlib>
 #include <vector>
 
@@ -48,7 +61,7 @@ struct MmaOp {                // offsets in 16-byte units
     uint16_t b_off;           // within the packed weights of this Cout tile
     uint16_t a_lbo;           // A leading-byte-offset (distance between the two 8-channel K chunks)
     uint8_t acc;              // accumulator index
-    uint8_t rd_first;         // bits 0-1: depth slab of the step (0..2); bit 7: overwrite the accumulator
+    uint8_t rd_first;         // depth slab of the step (0..2)
 };
 
 struct AccOut {               // where accumulator `acc` lands: od = od_mul*step + dd, oh = oh_mul*(h0+th) + dh
@@ -89,17 +102,9 @@ struct PackPlan {
 // ---- device helpers (inline PTX; sm_100a) -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_units, uint32_t sbo_units)
-{
-    // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48)
-    // | base_offset[49,52)=0 | lbo_mode[52]=0 | layout_type[61,64)=0 (SWIZZLE_NONE / interleave)
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)(lbo_units & 0x3FFF) << 16;
-    d |= (uint64_t)(sbo_units & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
+// SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48)
+// | base_offset[49,52)=0 | lbo_mode[52]=0 | layout_type[61,64)=0 (SWIZZLE_NONE / interleave); all in 16 B
+// units.  The issue loop assembles it as (kDescHi << 32) | (start + LBO << 16).
 
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n)
 {
@@ -114,17 +119,6 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t a_desc, u
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
         :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
-}
-
-// Same, but predicated on `issue` INSIDE the PTX: no C++ branch around the instruction, so the compiler
-// emits no BSSY/BSYNC reconvergence pair per MMA in the (warp-uniform) issue loop.
-__device__ __forceinline__ void umma_bf16_ss_if(uint32_t issue, uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
-                                                uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue));
 }
 
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
@@ -176,19 +170,6 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
-{
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // TMEM loads WITHOUT the wait: issue several, then tmem_wait_ld() once.
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16])

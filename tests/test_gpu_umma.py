@@ -110,3 +110,41 @@ def test_cas_cascade_fast_vs_golden():
     for s in ("stage1", "stage2", "stage3"):
         rel = np.abs(out[s]["depth"].cpu().numpy() - g[s + "_depth"]) / g[s + "_depth"]
         assert rel.max() < 2e-3, (s, rel.max())
+
+
+def test_cfg2_mvsnet_full_size_fast_vs_strict():
+    """BASELINE cfg2 shape (MVSNet, features 32x128x160, N=5, D=192, B>1): whole hot path on the fast
+    (C8 bf16 + tcgen05) path vs the strict fp32 path on the same bf16-representable inputs."""
+    from mvs_b200 import modules
+    B, N, D, H, W = 2, 5, 192, 128, 160
+    sd = cases.costreg_state("mvsnet", seed=70)
+    def make(mode):
+        net = modules.CostRegNetMVSNet(mode=mode)
+        net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+        return net.to(DEV).eval()
+    feats = [cu(f).bfloat16().float() for f in cases.synth.features(N, 32, H, W, 71, B)]
+    proj = cu(cases.synth.proj_matrices(N, W, 72, B))
+    depth = cu(np.tile((425.0 + 2.65 * np.arange(D)).astype(np.float32), (B, 1)))
+    with torch.no_grad():
+        ref = modules.mvsnet_hot_path(feats, proj, depth, make("strict"))
+        out = modules.mvsnet_hot_path(feats, proj, depth, make("fast"))
+    rel = ((out["depth"] - ref["depth"]).abs() / ref["depth"]).max().item()
+    assert rel < 5e-3, rel
+    assert (out["photometric_confidence"] - ref["photometric_confidence"]).abs().max().item() < 0.05
+
+
+def test_cfg5_builder_seven_views_full_size():
+    """BASELINE cfg5 stage-3 shape (C=8, D=8, 1056x1920, N=7 => 6 source views): C8 builder vs the
+    strict builder on bf16-representable features (one bf16 rounding of the result + fp32 reassociation)."""
+    from mvs_b200 import ops
+    N, C, D, H, W = 7, 8, 8, 1056, 1920
+    torch.manual_seed(5)
+    feats = [torch.randn(1, C, H, W, device=DEV).bfloat16().float() for _ in range(N)]
+    p = torch.from_numpy(cases.synth.proj_matrices(N, W, 73, 1))
+    prod = torch.stack([p[:, i] @ torch.inverse(p[:, 0]) for i in range(1, N)], 1)
+    rots = [prod[:, i, :3, :3].reshape(1, 9).contiguous().to(DEV) for i in range(N - 1)]
+    trs = [prod[:, i, :3, 3].contiguous().to(DEV) for i in range(N - 1)]
+    depth = cu(cases.synth.depth_per_pixel(D, H, W, 2.65, 1))
+    strict = ops.cost_volume(feats[0], feats[1:], rots, trs, depth)
+    fast = ops.unpack_c8(ops.cost_volume_c8(ops.pack_c8(feats[0]), [ops.pack_c8(f) for f in feats[1:]], rots, trs, depth), C)
+    assert ((fast - strict).abs() <= strict.abs() * 2 ** -7 + 2e-3).all()
