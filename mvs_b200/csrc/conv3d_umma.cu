@@ -78,7 +78,11 @@ struct ConvPlan {
     int cin_chunks, cout, cout_chunks, n, cout_tiles;
     int mode, ht, rh, arr, rd, ring;
     int slab_units, weight_units, tmem_cols, acc_cols;
-    int h_mul, h_base;        // h_in(r) = h_mul * h0 + h_base + r          (h0 = ht * blockIdx.y)
+    // Internally the kernel walks a "step" axis (slabs, named d below) and tiles a "row" axis (named h).
+    // swap = 1 maps step -> real H and row -> real D (every stage then has tens of steps per CTA even
+    // when D is 1..8); D, H, Do, Ho above are the INTERNAL extents, Dr/Hr/Dor/Hor the real ones.
+    int swap, Dr, Hr, Dor, Hor, row_blocks, steps_per_cta;
+    int h_mul, h_base;        // h_in(r) = h_mul * h0 + h_base + r          (h0 = ht * row block)
     int d_mul, d_base;        // d_in(slab i) = d_base + i ; step s uses slabs d_mul*s + {0..rd-1}
     int w_step, w_base[2];    // w_in(arr, col) = w_step * (m0 + col) + w_base[arr]
     int od_mul, oh_mul, w_mul;
@@ -219,7 +223,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch, issuer id)
     const int m0 = blockIdx.x * 128;
-    const int h0 = blockIdx.y * P.ht;
+    const int h0 = (int)(blockIdx.y % (unsigned)P.row_blocks) * P.ht;
+    const int step_begin = (int)(blockIdx.y / (unsigned)P.row_blocks) * P.steps_per_cta;      // this CTA's chunk of the step axis
+    const int nsteps = min(P.steps - step_begin, P.steps_per_cta);
     const int b = blockIdx.z / P.cout_tiles, ct = blockIdx.z % P.cout_tiles;
 
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
@@ -244,13 +250,13 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = *tmem_slot;
-    const int n_slabs = P.d_mul * (P.steps - 1) + P.rd;              // depth slabs this CTA stages in total
+    const int n_slabs = P.d_mul * (nsteps - 1) + P.rd;               // slabs this CTA stages in total
 
     if (warp >= 4 && warp < 8) {
         // =========================== producers: global -> shared (cp.async) ===========================
         const int pwarp = warp - 4;
         const int lines = P.rh * P.cin_chunks * P.arr;                // lines of UM_COLS 16-byte vectors per slab
-        const size_t plane_in = (size_t)P.H * P.W;
+        const size_t plane_in = (size_t)P.Hr * P.W;
         int pending = -1;              // slab staged (cp.async committed) but not yet published
         for (int i = 0; i < n_slabs; ++i) {
             const int slot = i % P.ring, q = i / P.ring;
@@ -265,15 +271,15 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 }
                 mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
             }
-            const int d_in = P.d_base + i;
+            const int d_in = P.d_base + P.d_mul * step_begin + i;
             const bool d_ok = d_in >= 0 && d_in < P.D;
             uint4 *slab = sa + (size_t)slot * P.slab_units;
             for (int ln = pwarp; ln < lines; ln += UM_PROD_THREADS / 32) {
                 const int a = ln % P.arr, chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
                 const int h_in = P.h_mul * h0 + P.h_base + r;
                 const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
-                const uint4 *src = x + (((size_t)b * P.cin_chunks + chunk) * P.D + (row_ok ? d_in : 0)) * plane_in +
-                                   (size_t)(row_ok ? h_in : 0) * P.W;
+                const int dr = row_ok ? (P.swap ? h_in : d_in) : 0, hr = row_ok ? (P.swap ? d_in : h_in) : 0;   // real (d, h)
+                const uint4 *src = x + (((size_t)b * P.cin_chunks + chunk) * P.Dr + dr) * plane_in + (size_t)hr * P.W;
                 uint4 *dst = slab + (size_t)ln * UM_COLS;
                 const int wb = P.w_step * m0 + P.w_base[a];
 #pragma unroll
@@ -318,7 +324,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const int step0 = P.merged ? iss : 0, dstep = P.merged ? P.n_issuers : 1;
             const int tbl = P.merged ? 0 : iss;
             int waited = 0;
-            for (int step = step0; step < P.steps; step += dstep) {
+            for (int step = step0; step < nsteps; step += dstep) {
                 const int first = P.d_mul * step;
                 // only slabs this step reads: an issuer that skips steps must not test the parity of a
                 // barrier whose slot may already have been released and refilled (the phase would alias)
@@ -375,7 +381,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         // =========================== epilogue: TMEM -> registers -> global ============================
         const int m = warp * 32 + lane;                               // row of the M tile owned by this thread
         const uint32_t lane_base = taddr + ((uint32_t)(warp * 32) << 16);
-        for (int step = 0; step < P.steps; ++step) {
+        for (int step = 0; step < nsteps; ++step) {
             const int buf = step & 1, use = step >> 1;
             mbar_wait(tfull + buf, (uint32_t)use & 1u);
             tc_fence_after();
@@ -384,7 +390,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 // any step <= `step` still reads the slabs this step retires
                 for (int k = 0; k < P.d_mul; ++k) mbar_arrive(empty + (P.d_mul * step + k) % P.ring);
             }
-            const size_t vol_o = (size_t)P.Do * P.Ho * P.Wo;
+            const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
             const uint32_t tcol0 = lane_base + (uint32_t)(buf * P.acc_cols);
             // affine + ReLU + skip + store of one 8-channel block held in v[0..7]
             auto store_chunk = [&](const uint32_t (&v)[8], int nloc, size_t oidx) {
@@ -416,11 +422,12 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             };
             auto out_pos = [&](int a, bool &ok) -> size_t {      // voxel index of accumulator a's row for this thread
                 const AccOut ao = P.acc[a];
-                const int od = P.od_mul * step + ao.dd;
+                const int od = P.od_mul * (step_begin + step) + ao.dd;
                 const int oh = P.oh_mul * (h0 + ao.th) + ao.dh;
                 const int ow = P.w_mul * (m0 + m) + ao.wadd;
                 ok = od < P.Do && oh < P.Ho && ow < P.Wo;
-                return ((size_t)od * P.Ho + oh) * P.Wo + ow;
+                const int odr = P.swap ? oh : od, ohr = P.swap ? od : oh;                 // real (d, h)
+                return ((size_t)odr * P.Hor + ohr) * P.Wo + ow;
             };
             if (P.out_f32) {
                 // `prob` layer: one real channel -> fp32 logits; four rows' single-column loads per wait
@@ -527,6 +534,15 @@ struct LayerGeom {
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// The kernel's step axis is the real H axis and its row axis the real D axis (see ConvPlan::swap).
+constexpr bool kStepAlongH = true;
+// real tap index from the internal (step-axis k, row-axis k, kw)
+static int tap_index(int k_step, int k_row, int kw)
+{
+    const int kd = kStepAlongH ? k_row : k_step, kh = kStepAlongH ? k_step : k_row;
+    return (kd * 3 + kh) * 3 + kw;
+}
+
 static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
 {
     LayerGeom g;
@@ -550,7 +566,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
         // kh-merged: a k-step is (kd, kw-group, cin pair); its B block holds the kh = 2, 1, 0 taps side by side,
         // so ONE MMA on input row i feeds output rows i-2 .. i (the A operand is fetched once for three rows)
         for (int kd = 0; kd < 3; ++kd) {
-            auto tap = [&](int kh, int kw) { return (kd * 3 + kh) * 3 + kw; };
+            auto tap = [&](int kh, int kw) { return tap_index(kd, kh, kw); };
             auto add3 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1) {
                 KStep k{kd, 0, 0, col, chunk, lbo, 0, {{0, 0}, {0, 0}}};
                 g.ks.push_back(k);
@@ -573,7 +589,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
     } else if (g.mode == UM_CONV_S2) {
         for (int kd = 0; kd < 3; ++kd)
             for (int kh = 0; kh < 3; ++kh) {
-                auto tap = [&](int kw) { return (kd * 3 + kh) * 3 + kw; };
+                auto tap = [&](int kw) { return tap_index(kd, kh, kw); };
                 // (array, column shift) of tap kw: kw=0 -> O[c], 1 -> E[c], 2 -> O[c+1]
                 const int arr_of[3] = {1, 0, 1};
                 const int col_of[3] = {0, 0, 1};
@@ -599,7 +615,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
                             if ((ph == 0) != (kh == 1)) continue;
                             for (int kw = 0; kw < 3; ++kw) {
                                 if ((pw == 0) != (kw == 1)) continue;
-                                const int t = (kd * 3 + kh) * 3 + kw;
+                                const int t = tap_index(kd, kh, kw);
                                 for (int s = 0; s < CH; s += 2) {
                                     const bool pair = s + 1 < CH;
                                     add(kd == 0 ? 1 : 0, kh == 0 ? 1 : 0, 0, kw == 0 ? 1 : 0, s, pair ? plane : 1,
@@ -817,12 +833,29 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     static thread_local ConvPlan P;
     size_t smem = 0;
     const bool out_f32 = Cout == 1;
-    if (!build_plan(P, g, B, Cin, Cout, D, H, W, stride, transposed, flags, out_f32, skip_c8 != nullptr, smem))
+    // internal (step, row) axes = real (H, D): the step axis is always the long one, chunked per CTA below
+    const int Di = kStepAlongH ? H : D, Hi = kStepAlongH ? D : H;
+    if (!build_plan(P, g, B, Cin, Cout, Di, Hi, W, stride, transposed, flags, out_f32, skip_c8 != nullptr, smem))
         return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_fwd: no tile configuration fits shared memory / TMEM for this layer");
     MVS_REQUIRE(!(out_f32 && skip_c8), "skip is not supported on the fp32 (Cout == 1) output");
-    const int rows_h = g.mode == UM_DECONV_S2 ? H : P.Ho;
+    P.swap = kStepAlongH ? 1 : 0;
+    P.Dr = D; P.Hr = H;
+    P.Dor = kStepAlongH ? P.Ho : P.Do;
+    P.Hor = kStepAlongH ? P.Do : P.Ho;
+    const int rows_h = g.mode == UM_DECONV_S2 ? Hi : P.Ho;
     const int m_ext = g.mode == UM_DECONV_S2 ? W : P.Wo;
-    dim3 grid(cdiv(m_ext, 128), cdiv(rows_h, P.ht), B * P.cout_tiles);
+    P.row_blocks = cdiv(rows_h, P.ht);
+    // chunk the step axis so the launch has >= ~4 CTAs per SM when the layer allows it, >= 16 steps per CTA
+    {
+        const long long base_ctas = (long long)cdiv(m_ext, 128) * P.row_blocks * B * P.cout_tiles;
+        long long chunks = (4 * 148 + base_ctas - 1) / base_ctas;
+        const long long max_chunks = P.steps / 16 > 1 ? P.steps / 16 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        P.steps_per_cta = cdiv(P.steps, chunks);
+    }
+    const int step_chunks = cdiv(P.steps, P.steps_per_cta);
+    dim3 grid(cdiv(m_ext, 128), (unsigned)(P.row_blocks * step_chunks), B * P.cout_tiles);
     MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "grid too large");
     cudaError_t e = cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
