@@ -845,11 +845,14 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     const int rows_h = g.mode == UM_DECONV_S2 ? Hi : P.Ho;
     const int m_ext = g.mode == UM_DECONV_S2 ? W : P.Wo;
     P.row_blocks = cdiv(rows_h, P.ht);
-    // chunk the step axis so the launch has >= ~4 CTAs per SM when the layer allows it, >= 16 steps per CTA
+    // chunk the step axis: aim for ~8 waves of CTAs (wave quantisation costs up to a whole wave otherwise),
+    // but keep chunks >= 8 steps (>= 4 when the layer is too small to fill the GPU) so pipeline fill amortises
     {
         const long long base_ctas = (long long)cdiv(m_ext, 128) * P.row_blocks * B * P.cout_tiles;
-        long long chunks = (4 * 148 + base_ctas - 1) / base_ctas;
-        const long long max_chunks = P.steps / 16 > 1 ? P.steps / 16 : 1;
+        const long long target = 8LL * 2 * 148;
+        long long chunks = (target + base_ctas - 1) / base_ctas;
+        const int min_steps = base_ctas * (P.steps / 8 > 0 ? P.steps / 8 : 1) < 2 * 148 ? 4 : 8;
+        const long long max_chunks = P.steps / min_steps > 1 ? P.steps / min_steps : 1;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
         P.steps_per_cta = cdiv(P.steps, chunks);
