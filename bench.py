@@ -139,6 +139,46 @@ def run_cpu_port(steps, warmup, rows):
                       f"width/D/C/N) per step, {len(times)} step(s), torch {torch.__version__} CPU, fp32"}
 
 
+def run_gpu_port(dev, steps, warmup, autocast):
+    """SURVEY.md §8(d) "reference GPU baseline beside it": the reference's op sequence
+    (oracle/torch_port.py = grid_sample + cuDNN conv3d + BN/ReLU + softmax, its stock code path) on
+    the same B200, full cfg3 ref view, cudnn.benchmark=True as the reference's train.py:25 sets it.
+    A reported baseline (checker code timed as the thing to beat), never on the product path."""
+    from oracle import torch_port as TP
+    feats, projs, dv = host_inputs()
+    tf = [{k: torch.from_numpy(a).to(dev) for k, a in f.items()} for f in feats]
+    tp = {k: torch.from_numpy(a).to(dev) for k, a in projs.items()}
+    sds = [{k: torch.from_numpy(np.asarray(a)).to(dev) for k, a in sd.items()} for sd in weights()]
+    tdv = torch.from_numpy(dv).to(dev)
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    out = {}
+    try:
+        for name, ac in (("fp32_tf32", False), ("autocast_bf16", True)):
+            if ac and not autocast:
+                continue
+            def one():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                    return TP.cas_cascade(tf, tp, tdv, sds, ndepths=NDEPTHS, img_hw=IMG_HW)
+            for _ in range(warmup):
+                one()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                one()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / steps
+            out[name] = {"value": 1e3 / ms, "ms_per_step": ms}
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    del tf, sds
+    torch.cuda.empty_cache()
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -270,6 +310,12 @@ def main_ours(args):
             dist.destroy_process_group()
         return
     cpu = run_cpu_port(1, 0, CPU_SAMPLE_ROWS) if (world == 1 and not args.no_cpu_baseline) else None
+    ref_gpu = None
+    if world == 1 and not args.no_ref_gpu:
+        try:
+            ref_gpu = run_gpu_port(dev, 5, 3, True)
+        except Exception as e:   # a reported side number must never take the bench line down
+            ref_gpu = {"error": f"{type(e).__name__}: {e}"[:200]}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "warp_variance_traffic.json")
     if os.path.exists(tpath):
@@ -295,6 +341,9 @@ def main_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                 "sample": cpu["sample"]}
+    if ref_gpu is not None:
+        line["ref_gpu_baseline"] = {"unit": UNIT, "what": "reference op sequence (grid_sample + cuDNN conv3d, oracle/torch_port.py) "
+                                    "on the same GPU, full cfg3 ref view, cudnn.benchmark=True, features resident", **ref_gpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -308,6 +357,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fast", choices=["strict", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-cuDNN side measurement")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

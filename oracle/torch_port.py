@@ -25,9 +25,10 @@ def warp_volume(src_fea, src_proj, ref_proj, depth_values, align_corners=None):
     with torch.no_grad():
         proj = src_proj @ torch.inverse(ref_proj)
         rot, trans = proj[:, :3, :3], proj[:, :3, 3:4]
-        ys, xs = torch.meshgrid(torch.arange(0, H, dtype=torch.float32), torch.arange(0, W, dtype=torch.float32),
-                                indexing="ij")
-        pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(H * W)))          # [3, H*W]
+        dev = src_fea.device
+        ys, xs = torch.meshgrid(torch.arange(0, H, dtype=torch.float32, device=dev),
+                                torch.arange(0, W, dtype=torch.float32, device=dev), indexing="ij")
+        pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(H * W, device=dev)))   # [3, H*W]
         rot_xyz = torch.matmul(rot, pix.unsqueeze(0).repeat(B, 1, 1))                   # [B, 3, H*W]
         pts = rot_xyz.unsqueeze(2).repeat(1, 1, D, 1) * depth_values.view(B, 1, D, -1)  # [B, 3, D, H*W]
         pts = pts + trans.view(B, 3, 1, 1)
@@ -108,7 +109,7 @@ def regress(cost_reg, depth_values, clamp_index):
     D = p.shape[1]
     with torch.no_grad():
         sum4 = 4 * F.avg_pool3d(F.pad(p.unsqueeze(1), pad=(0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
-        idx = torch.sum(p * torch.arange(D, dtype=torch.float).view(1, D, 1, 1), 1).long()
+        idx = torch.sum(p * torch.arange(D, dtype=torch.float, device=p.device).view(1, D, 1, 1), 1).long()
         if clamp_index:
             idx = idx.clamp(min=0, max=D - 1)
         conf = torch.gather(sum4, 1, idx.unsqueeze(1)).squeeze(1)
@@ -142,14 +143,14 @@ def cas_cascade(features, proj_matrices, depth_values, sds, ndepths=(48, 32, 8),
         if depth is None:
             lo, hi = depth_values[:, 0], depth_values[:, -1]
             step = (hi - lo) / (nd - 1)
-            samples = lo.unsqueeze(1) + torch.arange(0, nd, dtype=lo.dtype).reshape(1, -1) * step.unsqueeze(1)
+            samples = lo.unsqueeze(1) + torch.arange(0, nd, dtype=lo.dtype, device=lo.device).reshape(1, -1) * step.unsqueeze(1)
             samples = samples.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, H, W)
         else:
             cur = F.interpolate(depth.detach().unsqueeze(1), [H, W], mode="bilinear", align_corners=False).squeeze(1)
             half = nd / 2 * (ratios[i] * depth_interval)
             lo, hi = cur - half, cur + half
             step = (hi - lo) / (nd - 1)
-            samples = lo.unsqueeze(1) + torch.arange(0, nd, dtype=cur.dtype).reshape(1, -1, 1, 1) * step.unsqueeze(1)
+            samples = lo.unsqueeze(1) + torch.arange(0, nd, dtype=cur.dtype, device=cur.device).reshape(1, -1, 1, 1) * step.unsqueeze(1)
         hyp = F.interpolate(samples.unsqueeze(1), [nd, H // scale, W // scale], mode="trilinear",
                             align_corners=False).squeeze(1)
         d, c = cas_stage([f[key] for f in features], proj_matrices[key], hyp, sds[i])
