@@ -849,9 +849,11 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     // but keep chunks >= 8 steps (>= 4 when the layer is too small to fill the GPU) so pipeline fill amortises
     {
         const long long base_ctas = (long long)cdiv(m_ext, 128) * P.row_blocks * B * P.cout_tiles;
-        const long long target = 8LL * 2 * 148;
+        static const int waves_env = getenv("MVS_UMMA_WAVES") ? atoi(getenv("MVS_UMMA_WAVES")) : 0;   // tuning knob
+        const long long target = (waves_env > 0 ? (long long)waves_env : 8LL * 2) * 148;
         long long chunks = (target + base_ctas - 1) / base_ctas;
-        const int min_steps = base_ctas * (P.steps / 8 > 0 ? P.steps / 8 : 1) < 2 * 148 ? 4 : 8;
+        static const int min_steps_env = getenv("MVS_UMMA_MIN_STEPS") ? atoi(getenv("MVS_UMMA_MIN_STEPS")) : 0;
+        const int min_steps = min_steps_env > 0 ? min_steps_env : (base_ctas * (P.steps / 8 > 0 ? P.steps / 8 : 1) < 2 * 148 ? 4 : 8);
         const long long max_chunks = P.steps / min_steps > 1 ? P.steps / min_steps : 1;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
