@@ -137,6 +137,11 @@ int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const float *scale
                       const void *skip_c8, void *y, int B, int Cin, int Cout, int D, int H, int W,
                       int stride, int transposed, int flags, void *stream);
 
+/* Profiling hook (tools/prof_conv_trace.py): when dev_buf != NULL, the first n_ctas CTAs of every following
+ * mvs_conv3d_c8_fwd launch from this host thread add their per-role clock64 timers to dev_buf[cta * 16 + k]
+ * (int64; k documented at RoleTimer in csrc/conv3d_umma.cu).  NULL switches it off.  Not part of the data path. */
+int mvs_conv3d_c8_set_trace(void *dev_buf, int n_ctas);
+
 /* ---- a4+a5+a6: softmax over D + soft-argmin depth + photometric confidence ---------------------
  * Replaces F.softmax(cost_reg, 1) + depth_regression + the pad/avg_pool3d/gather confidence:
  *   MVSNet/models/mvsnet.py:183-191, module.py:91-103; CasMVSNet/models/cas_mvsnet.py:51-64

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mvs_conv3d_c8_packed_weight_bytes": (_i64, [_i] * 4),
     "mvs_conv3d_c8_pack_weights": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
     "mvs_conv3d_c8_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
+    "mvs_conv3d_c8_set_trace": (_i, [_vp, _i]),
     "mvs_softargmin_conf_fwd": (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i] * 5 + [_vp]),
     "mvs_depth_range_samples": (_i, [_vp, _d, _i, _vp, _i, _i, _i, _vp]),
     "mvs_cas_hypotheses": (_i, [_vp] + [_i] * 7 + [_d, _vp, _i, _vp]),

@@ -48,11 +48,13 @@ constexpr int UM_EPI_THREADS = 128;
 constexpr int UM_PROD_THREADS = 128;
 constexpr int UM_MAX_ISSUERS = 4;
 constexpr int UM_THREADS = UM_EPI_THREADS + UM_PROD_THREADS + 32 * UM_MAX_ISSUERS;
+constexpr int UM_THREADS_TM = UM_THREADS + UM_EPI_THREADS;     // T-merged kernel: + a second epilogue group (warps 12-15)
 constexpr int UM_COLS = 132;        // staged columns per row (128 + halo + pairing pad)
 constexpr int UM_MAX_OPS = 224;
 constexpr int UM_MAX_ACC = 16;
 constexpr int UM_MAX_KSTEPS = 112;
-constexpr int UM_MAX_RING = 6;
+constexpr int UM_MAX_RING = 8;
+constexpr int UM_TBUFS = 4;         // per-slab accumulator buffers of the T-merged mode
 
 enum UmMode { UM_CONV_S1 = 0, UM_CONV_S2 = 1, UM_DECONV_S2 = 2 };
 
@@ -90,6 +92,12 @@ struct ConvPlan {
     int relu, out_f32, has_skip;
     int n_issuers, zero_units;                      // zero_units: 16 B units of the all-zero B block (merged mode)
     int merged;                                     // stride-1 kh-merged mode: 2 issuers alternate depth steps, epilogue frees slabs
+    // T-merged mode (stride 1): ONE MMA per (input row, k-step) carries all nine (row tap, step tap) weights along N,
+    // each slab is read once; accumulators live in a ring of 4 per-slab TMEM buffers laid out [row][step tap][n] and
+    // the epilogue adds the three step-tap partials of an output step (slabs s, s+1, s+2).
+    long long *trace;                               // profiling hook (mvs_conv3d_c8_set_trace): per-CTA role timers, or null
+    int trace_ctas;
+    int tmerged, buf_cols, prefetch;                // prefetch: slabs in flight per producer thread (<= ring - 1)
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
@@ -100,6 +108,7 @@ struct ConvPlan {
 
 struct PackPlan {
     int cin, cout, n, cout_tiles, n_ksteps, nblk, transposed_weights, flip;
+    int pad_rows;                 // all-zero rows appended to every chunk of a B block (T-merged, n = 8)
     KStepSrc ks[UM_MAX_KSTEPS];   // [n_ksteps * nblk]: weight source of block `blk` of k-step `k` at [k * nblk + blk]
 };
 
@@ -153,6 +162,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Role timers of the profiling hook: slot k of CTA c accumulates clock64 deltas at trace[c * 16 + k].
+//   0 CTA total | 1 producer wait empty | 2 producer stage+publish | 3 issuer wait full | 4 issuer wait tempty
+//   5 issuer issue | 6 epilogue wait tfull | 7 epilogue work | 8 steps | 9 prologue (until roles start)
+struct RoleTimer {
+    long long *p; long long t;
+    __device__ __forceinline__ void start(bool on, long long *base) { p = on ? base : nullptr; if (p) t = clock64(); }
+    __device__ __forceinline__ void lap(int k) { if (p) { const long long n = clock64(); p[k] += n - t; t = n; } }
+};
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
@@ -172,8 +198,32 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t 
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): completion is reported to `bar` as `bytes` of tx-count
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+// wait until at most n (0..6) of the most recently committed groups are still pending
+__device__ __forceinline__ void cp_async_wait_dyn(int n)
+{
+    switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    default: cp_async_wait<6>(); break;
+    }
+}
 
 // TMEM loads WITHOUT the wait: issue several, then tmem_wait_ld() once.
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16])
@@ -203,7 +253,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UM_THREADS)
+template <bool TM>
+__global__ void __launch_bounds__(TM ? UM_THREADS_TM : UM_THREADS)
 conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__ x, const uint4 *__restrict__ wpk,
                    const float *__restrict__ scale, const float *__restrict__ shift, const uint4 *__restrict__ skip,
                    void *__restrict__ y)
@@ -214,9 +265,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     uint64_t *bars = reinterpret_cast<uint64_t *>(sa + (size_t)P.ring * P.slab_units);
     uint64_t *full = bars;                       // [ring]  slab landed            (128 producer arrivals)
     uint64_t *empty = bars + UM_MAX_RING;        // [ring]  slab no longer read     (1 tcgen05.commit)
-    uint64_t *tfull = bars + 2 * UM_MAX_RING;    // [2]     accumulators complete   (1 tcgen05.commit)
-    uint64_t *tempty = tfull + 2;                // [2]     accumulators drained    (128 epilogue arrivals)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *tfull = bars + 2 * UM_MAX_RING;    // [4]     accumulators complete   (1 tcgen05.commit)
+    uint64_t *tempty = tfull + UM_TBUFS;         // [4]     accumulators drained    (128 epilogue arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + UM_TBUFS);
     float *s_scale = reinterpret_cast<float *>(tmem_slot + 4);       // [n] folded-BN scale of this Cout tile (0 for padding)
     float *s_shift = s_scale + 32;                                   // [n] shift
 
@@ -228,17 +279,21 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     const int nsteps = min(P.steps - step_begin, P.steps_per_cta);
     const int b = blockIdx.z / P.cout_tiles, ct = blockIdx.z % P.cout_tiles;
 
+    const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    long long *trace = (P.trace && cta_lin < P.trace_ctas) ? P.trace + (size_t)cta_lin * 16 : nullptr;
+    const long long t_cta0 = trace ? clock64() : 0;
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     if (tid == 32) {
-        const uint32_t n_commit = P.merged ? 1u : (uint32_t)P.n_issuers;
-        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, UM_PROD_THREADS); mbar_init(empty + i, n_commit); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, n_commit); mbar_init(tempty + i, UM_EPI_THREADS); }
+        const uint32_t n_commit = (P.merged || TM) ? 1u : (uint32_t)P.n_issuers;
+        // T-merged: slabs arrive by bulk copies (tx bytes) + one arrival per producer warp
+        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, TM ? UM_PROD_THREADS / 32 : UM_PROD_THREADS); mbar_init(empty + i, n_commit); }
+        for (int i = 0; i < UM_TBUFS; ++i) { mbar_init(tfull + i, n_commit); mbar_init(tempty + i, TM ? 2 * UM_EPI_THREADS : UM_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     {   // weights: staged once per CTA
         const uint4 *src = wpk + (size_t)ct * P.weight_units;
-        for (int i = tid; i < P.weight_units; i += UM_THREADS) sw[i] = __ldg(src + i);
-        for (int i = tid; i < P.zero_units; i += UM_THREADS) sw[P.weight_units + i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < P.weight_units; i += (TM ? UM_THREADS_TM : UM_THREADS)) sw[i] = __ldg(src + i);
+        for (int i = tid; i < P.zero_units; i += (TM ? UM_THREADS_TM : UM_THREADS)) sw[P.weight_units + i] = make_uint4(0, 0, 0, 0);
     }
     if (tid < P.n) {   // epilogue affine of this Cout tile; padded channels get (0, 0) so they store 0
         const int c = ct * P.n + tid;
@@ -250,14 +305,200 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = *tmem_slot;
-    const int n_slabs = P.d_mul * (nsteps - 1) + P.rd;               // slabs this CTA stages in total
+    if (trace && tid == 0) { trace[9] = clock64() - t_cta0; trace[8] = nsteps; }
+    const int n_slabs = TM ? nsteps + 2 : P.d_mul * (nsteps - 1) + P.rd;   // slabs this CTA stages in total
 
+    if (TM && (warp < 4 || warp >= 12)) {
+        // =========================== T-merged epilogue: TMEM -> registers -> global =====================
+        // Two groups of four warps (a warp may only read the TMEM lanes 32 (warp % 4) ..): group g takes the rows
+        // g, g+2, ...  An output step adds the step-tap partials of slabs step, step+1, step+2.  Work items
+        // (row, 8-channel block) are processed two at a time so that six TMEM loads are in flight per wait.
+        const int eg = warp >= 12 ? 1 : 0, ew = warp & 3;
+        const int m = ew * 32 + lane;                                 // row of the M tile owned by this thread
+        const uint32_t lane_base = taddr + ((uint32_t)(ew * 32) << 16);
+        const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
+        const int n3 = 3 * P.n, nb = P.n >> 3;
+        const int my_rows = (P.ht - eg + 1) >> 1, n_items = my_rows * nb;
+        const int ow = m0 + m;
+        RoleTimer rt; rt.start(trace && tid == 0, trace);
+        for (int step = 0; step < nsteps; ++step) {
+            // earlier slabs were waited for in earlier steps
+            for (int sl = step == 0 ? 0 : step + 2; sl <= step + 2; ++sl)
+                mbar_wait(tfull + (sl & (UM_TBUFS - 1)), (uint32_t)(sl / UM_TBUFS) & 1u);
+            rt.lap(6);
+            tc_fence_after();
+            uint32_t tcol[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                tcol[t] = lane_base + (uint32_t)(((step + t) & (UM_TBUFS - 1)) * P.buf_cols + t * P.n);
+            const int od = step_begin + step;
+            auto row_pos = [&](int a, bool &ok) -> size_t {
+                const int oh = h0 + a;
+                ok = od < P.Do && oh < P.Ho && ow < P.Wo;
+                const int odr = P.swap ? oh : od, ohr = P.swap ? od : oh;                 // real (d, h)
+                return ((size_t)odr * P.Hor + ohr) * P.Wo + ow;
+            };
+            if (P.out_f32) {
+                // `prob`: one real channel -> fp32 logits; up to four rows (12 single-column loads) per wait
+                for (int j0 = 0; j0 < my_rows; j0 += 4) {
+                    uint32_t r[4][3];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j0 + j < my_rows) {
+                            const uint32_t c0 = (uint32_t)((eg + 2 * (j0 + j)) * n3);
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) tmem_ld1_nowait(tcol[t] + c0, r[j][t]);
+                        }
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j0 + j >= my_rows) break;
+                        bool ok;
+                        const size_t pos = row_pos(eg + 2 * (j0 + j), ok);
+                        if (!ok) continue;
+                        const float acc = (__uint_as_float(r[j][0]) + __uint_as_float(r[j][1])) + __uint_as_float(r[j][2]);
+                        float o = fmaf(acc, s_scale[0], s_shift[0]);
+                        if (P.relu) o = fmaxf(o, 0.f);
+                        reinterpret_cast<float *>(y)[(size_t)b * vol_o + pos] = o;
+                    }
+                }
+            } else {
+                auto finish = [&](const uint32_t (&r0)[8], const uint32_t (&r1)[8], const uint32_t (&r2)[8], int a, int n0) {
+                    bool ok;
+                    const size_t pos = row_pos(a, ok);
+                    const int cc = ct * P.n + n0;
+                    if (!ok || cc >= P.cout_chunks * 8) return;
+                    const size_t oidx = ((size_t)b * P.cout_chunks + (cc >> 3)) * vol_o + pos;
+                    uint4 sk = make_uint4(0, 0, 0, 0);
+                    if (P.has_skip) sk = __ldg(skip + oidx);
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + n0);
+                    const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + n0);
+                    const float4 sa = sc4[0], sb = sc4[1], ha = sh4[0], hb = sh4[1];
+                    const float2 sc2[4] = {{sa.x, sa.y}, {sa.z, sa.w}, {sb.x, sb.y}, {sb.z, sb.w}};
+                    const float2 sh2[4] = {{ha.x, ha.y}, {ha.z, ha.w}, {hb.x, hb.y}, {hb.z, hb.w}};
+                    const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 v = __fadd2_rn(make_float2(__uint_as_float(r0[2 * e]), __uint_as_float(r0[2 * e + 1])),
+                                              make_float2(__uint_as_float(r1[2 * e]), __uint_as_float(r1[2 * e + 1])));
+                        v = __fadd2_rn(v, make_float2(__uint_as_float(r2[2 * e]), __uint_as_float(r2[2 * e + 1])));
+                        v = __ffma2_rn(v, sc2[e], sh2[e]);
+                        if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                        if (P.has_skip) {
+                            v.x += __uint_as_float(sv[e] << 16);
+                            v.y += __uint_as_float(sv[e] & 0xffff0000u);
+                        }
+                        pk[e] = pack_bf16x2(v.x, v.y);
+                    }
+                    reinterpret_cast<uint4 *>(y)[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                };
+                for (int it = 0; it < n_items; it += 2) {
+                    const int a0 = eg + 2 * (it / nb), n00 = (it % nb) * 8;
+                    const bool two = it + 1 < n_items;
+                    const int a1 = eg + 2 * ((it + 1) / nb), n01 = ((it + 1) % nb) * 8;
+                    uint32_t p0[8], p1[8], p2[8], q0[8], q1[8], q2[8];
+                    const uint32_t c0 = (uint32_t)(a0 * n3 + n00), c1 = (uint32_t)(a1 * n3 + n01);
+                    tmem_ld8_nowait(tcol[0] + c0, p0);
+                    tmem_ld8_nowait(tcol[1] + c0, p1);
+                    tmem_ld8_nowait(tcol[2] + c0, p2);
+                    if (two) {
+                        tmem_ld8_nowait(tcol[0] + c1, q0);
+                        tmem_ld8_nowait(tcol[1] + c1, q1);
+                        tmem_ld8_nowait(tcol[2] + c1, q2);
+                    }
+                    tmem_wait_ld();
+                    finish(p0, p1, p2, a0, n00);
+                    if (two) finish(q0, q1, q2, a1, n01);
+                }
+            }
+            tc_fence_before();                                     // this thread's TMEM reads are complete ...
+            mbar_arrive(tempty + (step & (UM_TBUFS - 1)));         // ... slab `step`'s buffer may be overwritten
+            rt.lap(7);
+        }
+    } else
     if (warp >= 4 && warp < 8) {
         // =========================== producers: global -> shared (cp.async) ===========================
         const int pwarp = warp - 4;
         const int lines = P.rh * P.cin_chunks * P.arr;                // lines of UM_COLS 16-byte vectors per slab
         const size_t plane_in = (size_t)P.Hr * P.W;
         int pending = -1;              // slab staged (cp.async committed) but not yet published
+        auto stage_slab = [&](int i, int slot) {
+            const int d_in = P.d_base + P.d_mul * step_begin + i;
+            const bool d_ok = d_in >= 0 && d_in < P.D;
+            uint4 *slab = sa + (size_t)slot * P.slab_units;
+            for (int ln = pwarp; ln < lines; ln += UM_PROD_THREADS / 32) {
+                const int a = ln % P.arr, chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
+                const int h_in = P.h_mul * h0 + P.h_base + r;
+                const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
+                const int dr = row_ok ? (P.swap ? h_in : d_in) : 0, hr = row_ok ? (P.swap ? d_in : h_in) : 0;   // real (d, h)
+                const uint4 *src = x + (((size_t)b * P.cin_chunks + chunk) * P.Dr + dr) * plane_in + (size_t)hr * P.W;
+                uint4 *dst = slab + (size_t)ln * UM_COLS;
+                const int wb = P.w_step * m0 + P.w_base[a];
+#pragma unroll
+                for (int cc = 0; cc < (UM_COLS + 31) / 32; ++cc) {
+                    const int c = cc * 32 + lane;
+                    if (c < UM_COLS) {
+                        const int w_in = P.w_step * c + wb;
+                        const bool ok = row_ok && w_in >= 0 && w_in < P.W;
+                        cp_async16(dst + c, src + (ok ? w_in : 0), ok ? 16u : 0u);
+                    }
+                }
+            }
+        };
+        if (TM) {
+            // A staged line (one row of one channel block, 132 consecutive voxels) is contiguous in global memory, so it
+            // moves as ONE bulk copy issued by one lane (lane l of producer warp p owns line p + 4 l); only the out-of-
+            // volume parts (halo rows / columns, slabs beyond the step axis) are zero-filled with ordinary stores.
+            // Everything but the slab index is hoisted, so an interior slab costs a barrier wait + one copy per lane.
+            RoleTimer rt; rt.start(trace && tid == 128, trace);
+            const int c_lo = m0 == 0 ? 1 : 0;                                  // column c holds w = m0 - 1 + c
+            const int c_hi = min(UM_COLS, P.W - m0 + 1);
+            const int ln = pwarp + (UM_PROD_THREADS / 32) * lane;
+            const int my_row = ln / P.cin_chunks, my_chunk = ln % P.cin_chunks;
+            const int my_h = h0 - 1 + my_row;
+            const bool my_ok = ln < lines && my_h >= 0 && my_h < P.H && c_hi > c_lo;
+            const uint32_t my_bytes = my_ok ? (uint32_t)(c_hi - c_lo) * 16u : 0u;
+            uint32_t warp_bytes = my_bytes;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) warp_bytes += __shfl_xor_sync(0xffffffffu, warp_bytes, o);
+            // source of this lane's line in slab 0 (d_in = d_base + step_begin) and its stride per slab
+            const size_t step_stride = P.swap ? (size_t)P.W : plane_in;
+            const uint4 *my_src = x + (((size_t)b * P.cin_chunks + my_chunk) * P.Dr + (P.swap ? (my_ok ? my_h : 0) : 0)) * plane_in
+                                  + (P.swap ? (size_t)0 : (size_t)(my_ok ? my_h : 0) * P.W) + (m0 - 1 + c_lo);
+            const uint32_t my_dst_off = (uint32_t)ln * UM_COLS + (uint32_t)c_lo;
+            // does any line of this warp need zero columns / zero rows in an in-range slab?
+            const bool edge_cols = c_lo > 0 || c_hi < UM_COLS;
+            const bool edge_rows = __any_sync(0xffffffffu, ln < lines && !(my_h >= 0 && my_h < P.H));
+            for (int i = 0; i < n_slabs; ++i) {
+                const int slot = i % P.ring, q = i / P.ring;
+                if (q >= 1) mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
+                rt.lap(1);
+                const int d_in = P.d_base + step_begin + i;
+                const bool d_ok = d_in >= 0 && d_in < P.D;
+                uint4 *slab = sa + (size_t)slot * P.slab_units;
+                if (!d_ok || edge_cols || edge_rows) {
+                    // zero the parts no copy will write (smem slots are recycled, so this is redone per slab)
+                    for (int l2 = pwarp; l2 < lines; l2 += UM_PROD_THREADS / 32) {
+                        const int h_in = h0 - 1 + l2 / P.cin_chunks;
+                        const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
+                        uint4 *dst = slab + (size_t)l2 * UM_COLS;
+                        if (!row_ok) {
+                            for (int c = lane; c < UM_COLS; c += 32) dst[c] = make_uint4(0, 0, 0, 0);
+                        } else {
+                            if (lane < c_lo) dst[lane] = make_uint4(0, 0, 0, 0);
+                            for (int c = c_hi + lane; c < UM_COLS; c += 32) dst[c] = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                }
+                if (lane == 0) mbar_arrive_expect_tx(full + slot, d_ok ? warp_bytes : 0u);
+                __syncwarp();
+                if (d_ok && my_bytes) bulk_copy_g2s(slab + my_dst_off, my_src + (size_t)d_in * step_stride, my_bytes, full + slot);
+                rt.lap(2);
+            }
+        } else
         for (int i = 0; i < n_slabs; ++i) {
             const int slot = i % P.ring, q = i / P.ring;
             if (q >= 1) {
@@ -305,7 +546,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             fence_async_smem();
             mbar_arrive(full + pending % P.ring);
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // =========================== MMA issuers ======================================================
         // Up to UM_MAX_ISSUERS warps, each owning a disjoint set of accumulators (independent chains).
         // A whole warp walks its slice of the op table on warp-uniform values (kernel-parameter table,
@@ -313,7 +554,61 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         // are predicated on one elected lane.  (Issuing from inside `if (lane == 0)` makes the compiler
         // wrap every UTCHMMA in an R2UR waterfall loop.)
         const int iss = warp - 8;
-        if (iss < P.n_issuers) {
+        if (TM) {
+            // ONE issuer walks the slabs in order: every slab is read once, by the MMAs of its own op table, into the
+            // slab's own TMEM buffer; the step-axis reduction happens in the epilogue.
+            // Two issuers alternate slabs (one warp's descriptor arithmetic costs ~85 clk per MMA, the tensor pipe needs
+            // ~45-70).  ring and UM_TBUFS are even, so a slab's smem slot and TMEM buffer always belong to the same
+            // issuer: every barrier is waited on by exactly one warp, phase after phase.
+            if (iss < 2) {
+                uint32_t leader;
+                asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
+                const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
+                const uint32_t idesc0 = umma_idesc_bf16(128, 0);
+                constexpr uint32_t kDescHi = 8u | (1u << 14);
+                RoleTimer rt; rt.start(trace && lane == 0 && iss == 0, trace);
+                for (int sl = iss; sl < n_slabs; sl += 2) {
+                    const int slot = sl % P.ring, buf = sl & (UM_TBUFS - 1), use = sl / UM_TBUFS;
+                    mbar_wait(full + slot, (uint32_t)(sl / P.ring) & 1u);
+                    rt.lap(3);
+                    if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
+                    rt.lap(4);
+                    tc_fence_after();
+                    const uint32_t tbase = taddr + (uint32_t)(buf * P.buf_cols);
+                    const uint32_t base = sa_units + (uint32_t)(slot * P.slab_units);
+                    int i = 0;
+                    for (; i + 4 <= P.n_ops; i += 4) {
+                        uint64_t ad[4], bd[4];
+                        uint32_t dc[4], ac[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 e = P.ops[i + j];
+                            ad[j] = ((uint64_t)kDescHi << 32) | (uint64_t)(e.x + base);
+                            bd[j] = ((uint64_t)kDescHi << 32) | (uint64_t)(e.y + sw_units);
+                            dc[j] = tbase + e.z;
+                            ac[j] = e.w;
+                        }
+                        if (leader) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                umma_bf16_ss(dc[j], ad[j], bd[j], idesc0 | ((ac[j] >> 8) << 17), ac[j] & 1u);
+                        }
+                    }
+                    for (; i < P.n_ops; ++i) {
+                        const uint4 e = P.ops[i];
+                        const uint64_t ad = ((uint64_t)kDescHi << 32) | (uint64_t)(e.x + base);
+                        const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(e.y + sw_units);
+                        if (leader) umma_bf16_ss(tbase + e.z, ad, bd, idesc0 | ((e.w >> 8) << 17), e.w & 1u);
+                    }
+                    if (leader) {
+                        umma_commit(empty + slot);     // the slab goes back to the producers once these MMAs retire
+                        umma_commit(tfull + buf);
+                    }
+                    __syncwarp();
+                    rt.lap(5);
+                }
+            }
+        } else if (iss < P.n_issuers) {
             uint32_t leader;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
             const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
@@ -489,6 +784,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     }
     tc_fence_before();
     __syncthreads();
+    if (trace && tid == 0) trace[0] = clock64() - t_cta0;
     if (warp == 0) tmem_dealloc(taddr, (uint32_t)P.tmem_cols);
 }
 
@@ -497,12 +793,14 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, __nv_bfloat16 *__restrict__ out)
 {
-    const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * P.nblk * P.n * 8;
+    const int rows_pc = P.nblk * P.n + P.pad_rows;               // rows per K chunk of a B block
+    const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * rows_pc * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long t = i;
         const int e = (int)(t % 8); t /= 8;
-        const int row = (int)(t % P.n); t /= P.n;
-        const int blk = (int)(t % P.nblk); t /= P.nblk;
+        const int rr = (int)(t % rows_pc); t /= rows_pc;
+        if (rr >= P.nblk * P.n) { out[i] = __float2bfloat16_rn(0.f); continue; }
+        const int row = rr % P.n, blk = rr / P.n;
         const int j = (int)(t % 2); t /= 2;
         const int ks = (int)(t % P.n_ksteps);
         const int ct = (int)(t / P.n_ksteps);
@@ -528,6 +826,7 @@ struct KStep {
 struct LayerGeom {
     int mode, cin_chunks, n, cout_tiles, arr;
     int nblk;                            // 3: stride-1 layers merge the three kh taps of an input row into one MMA
+    int tmerged, pad_rows;               // T-merged: nblk = 9 (row tap 2,1,0 major, step tap 0,1,2 minor) [+ zero rows]
     std::vector<KStep> ks;
     std::vector<KStepSrc> srcs;          // [ks.size() * nblk]
 };
@@ -562,6 +861,40 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
         g.srcs.push_back(k.src);
     };
     g.nblk = g.mode == UM_CONV_S1 ? 3 : 1;
+    g.tmerged = 0; g.pad_rows = 0;
+    static const int no_tmerged = getenv("MVS_UMMA_NO_TMERGED") ? atoi(getenv("MVS_UMMA_NO_TMERGED")) : 0;   // A/B knob
+    if (g.mode == UM_CONV_S1 && n_full <= 32 && !no_tmerged) {
+        // T-merged candidate: n = 8 for Cout <= 8 (N = rows*24 is padded to a multiple of 16 with 8 zero B rows),
+        // else n = Cout padded to 16.  Taken when the packed weights + a 3-deep ring of 3-row slabs fit shared memory.
+        const int n = Cout <= 8 ? 8 : n_full;
+        const int pad = n == 8 ? 8 : 0;
+        const int ksteps = CH == 1 ? 2 : 3 * ((CH + 1) / 2);
+        const size_t wbytes = (size_t)ksteps * 2 * (9 * n + pad) * 16, slab3 = (size_t)3 * CH * UM_COLS * 16;
+        if (wbytes + 3 * slab3 + 4096 <= 226 * 1024 && ksteps * 9 <= UM_MAX_KSTEPS) {
+            g.tmerged = 1; g.pad_rows = pad; g.n = n; g.cout_tiles = 1; g.nblk = 9;
+            auto add9 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1) {
+                KStep k{0, 0, 0, col, chunk, lbo, 0, {{0, 0}, {0, 0}}};
+                g.ks.push_back(k);
+                for (int krow = 2; krow >= 0; --krow)
+                    for (int t = 0; t < 3; ++t) {
+                        KStepSrc sc{{(int8_t)tap_index(t, krow, kw0), (int8_t)(kw1 >= 0 ? tap_index(t, krow, kw1) : -1)},
+                                    {(int8_t)ch0, (int8_t)ch1}};
+                        g.srcs.push_back(sc);
+                    }
+            };
+            if (CH == 1) {
+                add9(0, 0, 1, 0, 0, 1, 0);        // taps kw = 0, 1 on adjacent staged columns (LBO = 16 B)
+                add9(2, 0, 1, 2, 0, -1, 0);       // tap kw = 2 paired with zero weights
+            } else {
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int sidx = 0; sidx < CH; sidx += 2) {
+                        const bool pair = sidx + 1 < CH;
+                        add9(kw, sidx, pair ? plane : 1, kw, sidx, pair ? kw : -1, sidx + 1);
+                    }
+            }
+            return g;
+        }
+    }
     if (g.mode == UM_CONV_S1) {
         // kh-merged: a k-step is (kd, kw-group, cin pair); its B block holds the kh = 2, 1, 0 taps side by side,
         // so ONE MMA on input row i feeds output rows i-2 .. i (the A operand is fetched once for three rows)
@@ -630,7 +963,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
 
 static size_t plan_smem_bytes(int weight_units, int ring, int slab_units)
 {
-    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 4) * 8 + 16 + 64 * 4;
+    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 2 * UM_TBUFS) * 8 + 16 + 64 * 4;
 }
 
 static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
@@ -641,6 +974,72 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     P.B = B; P.D = D; P.H = H; P.W = W;
     const bool deconv = g.mode == UM_DECONV_S2;
     const bool merged = g.nblk == 3;                 // stride-1 conv: kh taps merged along N
+    if (g.tmerged) {
+        P.Do = D; P.Ho = H; P.Wo = W;
+        P.cin_chunks = g.cin_chunks; P.cout = Cout; P.cout_chunks = (Cout + 7) / 8; P.n = g.n; P.cout_tiles = 1;
+        P.mode = g.mode; P.arr = 1; P.tmerged = 1;
+        P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip;
+        P.rd = 3; P.d_mul = 1;
+        const int rows_pc = 9 * g.n + g.pad_rows, n3 = 3 * g.n;
+        const int packed_units = (int)g.ks.size() * 2 * rows_pc;
+        // rows per CTA: minimise the staged (and multiplied) rows, row_blocks * (ht + 2); ring: as deep as fits
+        int best = 0, best_ring = 0;
+        long long best_cost = -1;
+        for (int ht = 8; ht >= 1; --ht) {
+            if (ht > H && ht > 1) continue;
+            const int buf_cols = round_up(ht * n3 + g.pad_rows, 16);
+            if (UM_TBUFS * buf_cols > 512 || buf_cols > 256) continue;
+            if ((int)g.ks.size() * (ht + 2) + 1 > UM_MAX_OPS) continue;
+            int ring = 0;
+            for (int r = UM_MAX_RING; r >= 2 && !ring; r -= 2)          // even: see the issuer role
+                if (plan_smem_bytes(packed_units + 2 * buf_cols, r, (ht + 2) * g.cin_chunks * UM_COLS) <= 226 * 1024) ring = r;
+            if (!ring) continue;
+            // a 2-deep ring leaves each issuer one slot: its next slab cannot load while the current one is multiplied
+            const long long cost = (long long)((H + ht - 1) / ht) * (ht + 2) * (ring < 4 ? 10 : 8);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ht; best_ring = ring; }
+        }
+        if (!best) return false;
+        P.ht = best; P.ring = best_ring; P.rh = P.ht + 2;
+        P.prefetch = P.ring - 1 < 5 ? P.ring - 1 : 5;
+        P.slab_units = P.rh * g.cin_chunks * UM_COLS;
+        P.buf_cols = round_up(P.ht * n3 + g.pad_rows, 16);
+        P.zero_units = 2 * P.buf_cols;
+        P.weight_units = packed_units;
+        smem_bytes = plan_smem_bytes(P.weight_units + P.zero_units, P.ring, P.slab_units);
+        P.n_acc = P.ht; P.acc_cols = P.buf_cols;
+        int cols = 32;
+        while (cols < UM_TBUFS * P.buf_cols) cols *= 2;
+        P.tmem_cols = cols;
+        P.h_mul = 1; P.h_base = -1; P.d_base = -1; P.w_step = 1; P.w_base[0] = -1; P.w_base[1] = -1;
+        P.od_mul = 1; P.oh_mul = 1; P.w_mul = 1; P.steps = P.Do;
+        P.n_issuers = 1;
+        auto entry = [&](int a_off, int a_lbo, int b_off, int b_lbo, int col, int n_mma, int accumulate) {
+            return make_uint4((uint32_t)a_off | ((uint32_t)a_lbo << 16), (uint32_t)b_off | ((uint32_t)b_lbo << 16), (uint32_t)col,
+                              (uint32_t)accumulate | ((uint32_t)(n_mma >> 3) << 8));
+        };
+        int n_ops = 0;
+        // zero-initialise the slab's whole buffer (A: any staged finite bytes, B: the zero block), then one MMA per
+        // (staged input row i, k-step): rows lo..hi of the tile get the row taps i - row, all three step taps at once
+        P.ops[n_ops++] = entry(0, 1, packed_units, P.buf_cols, 0, P.buf_cols, 0);
+        for (int i = 0; i < P.rh; ++i) {
+            const int lo = i - 2 < 0 ? 0 : i - 2, hi = i > P.ht - 1 ? P.ht - 1 : i;
+            if (hi < lo) continue;
+            const int cnt = hi - lo + 1, blk0 = 2 - (i - lo);
+            for (size_t k = 0; k < g.ks.size(); ++k) {
+                const KStep &ks = g.ks[k];
+                const int a_off = (i * g.cin_chunks + ks.chunk) * UM_COLS + ks.col;
+                const int b_off = (int)k * 2 * rows_pc + blk0 * n3;
+                // N is rounded up to a multiple of 16 (n = 8 only): the extra 8 columns either read the zero pad rows
+                // of the B block or land in the spare columns behind the last row of this buffer
+                const int n_mma = round_up(cnt * n3, 16);
+                if (ks.lbo > 0x3FFF || a_off > 0xFFFF || b_off > 0x3FFF || rows_pc > 0x3FFF) return false;
+                if (lo * n3 + n_mma > P.buf_cols) return false;
+                P.ops[n_ops++] = entry(a_off, ks.lbo, b_off, rows_pc, lo * n3, n_mma, 1);
+            }
+        }
+        P.n_ops = n_ops;
+        return true;
+    }
     if (deconv) { P.Do = 2 * D; P.Ho = 2 * H; P.Wo = 2 * W; }
     else if (g.mode == UM_CONV_S2) { P.Do = (D - 1) / 2 + 1; P.Ho = (H - 1) / 2 + 1; P.Wo = (W - 1) / 2 + 1; }
     else { P.Do = D; P.Ho = H; P.Wo = W; }
@@ -794,11 +1193,21 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
 
 using namespace mvs;
 
+static thread_local long long *g_trace = nullptr;
+static thread_local int g_trace_ctas = 0;
+
+extern "C" int mvs_conv3d_c8_set_trace(void *dev_buf, int n_ctas)
+{
+    g_trace = (long long *)dev_buf;
+    g_trace_ctas = dev_buf ? n_ctas : 0;
+    return MVS_OK;
+}
+
 extern "C" int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stride, int transposed)
 {
     if (Cin <= 0 || Cout <= 0 || (stride != 1 && stride != 2)) return -1;
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
-    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * g.nblk * g.n * 16;
+    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * (g.nblk * g.n + g.pad_rows) * 16;
 }
 
 extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride, int transposed,
@@ -814,7 +1223,8 @@ extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin,
     pp.transposed_weights = transposed ? 1 : 0;
     pp.flip = (transposed && stride == 1) ? 1 : 0;       // ConvTranspose3d(stride 1, pad 1) == conv with flipped taps
     for (size_t k = 0; k < g.srcs.size(); ++k) pp.ks[k] = g.srcs[k];
-    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * g.nblk * g.n * 8;
+    pp.pad_rows = g.pad_rows;
+    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * (g.nblk * g.n + g.pad_rows) * 8;
     pack_weights_kernel<<<cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         pp, w, (__nv_bfloat16 *)packed);
     return check_launch("mvs_conv3d_c8_pack_weights");
@@ -838,6 +1248,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     if (!build_plan(P, g, B, Cin, Cout, Di, Hi, W, stride, transposed, flags, out_f32, skip_c8 != nullptr, smem))
         return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_fwd: no tile configuration fits shared memory / TMEM for this layer");
     MVS_REQUIRE(!(out_f32 && skip_c8), "skip is not supported on the fp32 (Cout == 1) output");
+    P.trace = g_trace; P.trace_ctas = g_trace_ctas;
     P.swap = kStepAlongH ? 1 : 0;
     P.Dr = D; P.Hr = H;
     P.Dor = kStepAlongH ? P.Ho : P.Do;
@@ -858,13 +1269,31 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
         P.steps_per_cta = cdiv(P.steps, chunks);
+        if (P.tmerged && waves_env == 0) {
+            // every CTA stages steps + 2 slabs and pays a pipeline fill (~2 steps) before its first store: pick the
+            // chunking that minimises waves x (steps per CTA + 4)
+            const long long slots = 148LL * (UM_TBUFS * P.buf_cols <= 256 && smem <= 112 * 1024 ? 2 : 1);
+            long long best_cost = -1;
+            for (int c = 1; c <= P.steps; ++c) {
+                const int spc = cdiv(P.steps, c);
+                if (spc < 4 && c > 1) break;
+                const long long ctas = base_ctas * cdiv(P.steps, spc);
+                const long long cost = cdiv(ctas, slots) * (spc + 4);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; P.steps_per_cta = spc; }
+            }
+        }
     }
     const int step_chunks = cdiv(P.steps, P.steps_per_cta);
     dim3 grid(cdiv(m_ext, 128), (unsigned)(P.row_blocks * step_chunks), B * P.cout_tiles);
     MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "grid too large");
-    cudaError_t e = cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = P.tmerged ? cudaFuncSetAttribute(conv3d_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(conv3d_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    conv3d_umma_kernel<<<grid, UM_THREADS, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed,
-                                                                         scale, shift, (const uint4 *)skip_c8, y);
+    if (P.tmerged)
+        conv3d_umma_kernel<true><<<grid, UM_THREADS_TM, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed,
+                                                                                      scale, shift, (const uint4 *)skip_c8, y);
+    else
+        conv3d_umma_kernel<false><<<grid, UM_THREADS, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed,
+                                                                                    scale, shift, (const uint4 *)skip_c8, y);
     return check_launch("mvs_conv3d_c8_fwd");
 }

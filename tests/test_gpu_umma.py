@@ -36,6 +36,14 @@ LAYERS = [
     (16, 8, 2, True, (3, 4, 130)),       # conv11: two M tiles
     (8, 1, 1, False, (4, 6, 133)),       # prob: fp32 logits out
     (64, 32, 1, True, (2, 4, 20)),       # CVP conv5: transposed stride 1
+    # T-merged stride-1 path (nine taps along N, step-axis reduction in the epilogue): several row blocks incl. a
+    # ragged one, more steps than TMEM buffers, interior rows with all three row taps
+    (32, 8, 1, False, (12, 21, 130)),
+    (16, 8, 1, False, (11, 9, 64)),
+    (8, 1, 1, False, (11, 19, 140)),
+    (16, 16, 1, False, (7, 18, 100)),
+    (32, 32, 1, False, (5, 11, 129)),
+    (16, 16, 1, True, (6, 10, 70)),      # transposed stride 1 (flipped taps) on the T-merged path
 ]
 
 

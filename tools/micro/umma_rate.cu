@@ -36,6 +36,17 @@ __global__ void __launch_bounds__(128) k(int N, int rot, int iters, int a_rot, i
         constexpr uint32_t kHi = 8u | (1u << 14);
         const uint32_t idesc = idesc_bf16(128, N);
         long long t0 = clock64();
+        if (rot == 1 && a_rot == 1 && !a_tmem) {
+            // descriptors hoisted: the loop body is nothing but UTCHMMA -> measures the pure dispatch / execution rate
+            const uint64_t ad = ((uint64_t)kHi << 32) | (uint64_t)(a_units + (132u << 16));
+            const uint64_t bd = ((uint64_t)kHi << 32) | (uint64_t)(b_units + ((uint32_t)N << 16));
+            if (leader) {
+#pragma unroll 8
+                for (int it = 0; it < iters; ++it)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                                 :: "r"(taddr), "l"(ad), "l"(bd), "r"(idesc), "r"(1u));
+            }
+        } else
         #pragma unroll 4
         for (int it = 0; it < iters; ++it) {
             const uint32_t acc = taddr + (uint32_t)((it & (rot - 1)) * N);

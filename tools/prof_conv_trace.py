@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Per-role timers of the T-merged UMMA conv (mvs_conv3d_c8_set_trace): where a CTA's time goes.
+
+    python tools/prof_conv_trace.py [--stages 1,2,3] [--layers conv0,prob]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from mvs_b200 import synth, ops, _lib
+from prof_conv import LAYERS
+
+NAMES = ["cta_total", "prod_wait_empty", "prod_stage", "iss_wait_full", "iss_wait_tempty", "iss_issue", "epi_wait_tfull",
+         "epi_work", "steps", "prologue"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stages", default="1,2,3")
+    ap.add_argument("--layers", default="conv0,conv2,conv4,prob")
+    ap.add_argument("--ctas", type=int, default=4096)
+    a = ap.parse_args()
+    dev = "cuda:0"
+    cfg = synth.CONFIGS["cfg3"]
+    lib = _lib.lib()
+    for si in [int(s) - 1 for s in a.stages.split(",")]:
+        c, d, h, w = cfg["stages"][si]
+        for name, cin_m, cout_m, stride, tr, lvl, has_skip in LAYERS:
+            if name not in a.layers.split(","):
+                continue
+            cin = c if cin_m is None else 8 * cin_m
+            cout = 1 if cout_m is None else 8 * cout_m
+            D, H, W = d >> lvl, h >> lvl, w >> lvl
+            x = torch.randn(1, (cin + 7) // 8, D, H, W, 8, device=dev).bfloat16()
+            wt = torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3), device=dev) / (27 * cin) ** 0.5
+            pk = ops.pack_conv_weights(wt, stride, tr)
+            fn = lambda: ops.conv3d_c8(x, pk, cin, cout, None, None, None, stride, tr, cout != 1)
+            fn(); fn()
+            buf = torch.zeros(a.ctas * 16, dtype=torch.int64, device=dev)
+            lib.mvs_conv3d_c8_set_trace(buf.data_ptr(), a.ctas)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            lib.mvs_conv3d_c8_set_trace(None, 0)
+            torch.cuda.synchronize()
+            t = buf.view(a.ctas, 16).cpu().double()
+            t = t[t[:, 0] > 0]
+            steps = t[:, 8].mean().item()
+            print(f"stage {si + 1} {name} cin={cin} cout={cout} {D}x{H}x{W}: {e0.elapsed_time(e1):.3f} ms, {len(t)} CTAs traced, "
+                  f"{steps:.1f} steps/CTA")
+            if len(t) == 0:
+                continue
+            for k, nm in enumerate(NAMES):
+                if nm == "steps":
+                    continue
+                print(f"    {nm:18s} {t[:, k].mean().item():10.0f} clk/CTA   {t[:, k].mean().item() / steps:8.0f} clk/step")
+
+
+if __name__ == "__main__":
+    main()
