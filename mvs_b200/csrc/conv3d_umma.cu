@@ -172,11 +172,15 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 
 // Role timers of the profiling hook: slot k of CTA c accumulates clock64 deltas at trace[c * 16 + k].
 //   0 CTA total | 1 producer wait empty | 2 producer stage+publish | 3 issuer wait full | 4 issuer wait tempty
-//   5 issuer issue | 6 epilogue wait tfull | 7 epilogue work | 8 steps | 9 prologue (until roles start)
-struct RoleTimer {
-    long long *p; long long t;
-    __device__ __forceinline__ void start(bool on, long long *base) { p = on ? base : nullptr; if (p) t = clock64(); }
-    __device__ __forceinline__ void lap(int k) { if (p) { const long long n = clock64(); p[k] += n - t; t = n; } }
+//   5 issuer issue | 6 epilogue wait tfull | 7 epilogue work | 9 prologue (until roles start) | 10 steps
+struct RoleTimer {          // accumulates in registers (a global read-modify-write per lap would cost ~700 clk each)
+    long long *p; long long t, a0, a1, a2;
+    int k0;
+    __device__ __forceinline__ void start(bool on, long long *base, int first_slot) { p = on ? base : nullptr; k0 = first_slot; a0 = a1 = a2 = 0; if (p) t = clock64(); }
+    __device__ __forceinline__ void lap(int k) {
+        if (p) { const long long n = clock64(); const long long d = n - t; t = n; const int j = k - k0; if (j == 0) a0 += d; else if (j == 1) a1 += d; else a2 += d; }
+    }
+    __device__ __forceinline__ void flush() { if (p) { p[k0] = a0; p[k0 + 1] = a1; if (k0 == 3) p[k0 + 2] = a2; } }
 };
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols)
@@ -305,7 +309,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = *tmem_slot;
-    if (trace && tid == 0) { trace[9] = clock64() - t_cta0; trace[8] = nsteps; }
+    if (trace && tid == 0) { trace[9] = clock64() - t_cta0; trace[10] = nsteps; }
     const int n_slabs = TM ? nsteps + 2 : P.d_mul * (nsteps - 1) + P.rd;   // slabs this CTA stages in total
 
     if (TM && (warp < 4 || warp >= 12)) {
@@ -320,7 +324,19 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int n3 = 3 * P.n, nb = P.n >> 3;
         const int my_rows = (P.ht - eg + 1) >> 1, n_items = my_rows * nb;
         const int ow = m0 + m;
-        RoleTimer rt; rt.start(trace && tid == 0, trace);
+        // output index of (row a, step): pos0 + a * row_stride + step * step_stride  (hoisted 64-bit arithmetic)
+        const size_t plane_o = (size_t)P.Hor * P.Wo;
+        const size_t row_stride = P.swap ? plane_o : (size_t)P.Wo, step_stride = P.swap ? (size_t)P.Wo : plane_o;
+        const size_t pos0 = (size_t)h0 * row_stride + (size_t)step_begin * step_stride + (size_t)ow;
+        const bool w_ok = ow < P.Wo;
+        // folded-BN affine of the first 8-channel block in registers (the only block when Cout <= 8)
+        float2 sc2[4], sh2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sc2[e] = make_float2(s_scale[2 * e], s_scale[2 * e + 1]);
+            sh2[e] = make_float2(s_shift[2 * e], s_shift[2 * e + 1]);
+        }
+        RoleTimer rt; rt.start(trace && tid == 0, trace, 6);
         for (int step = 0; step < nsteps; ++step) {
             // earlier slabs were waited for in earlier steps
             for (int sl = step == 0 ? 0 : step + 2; sl <= step + 2; ++sl)
@@ -331,15 +347,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 #pragma unroll
             for (int t = 0; t < 3; ++t)
                 tcol[t] = lane_base + (uint32_t)(((step + t) & (UM_TBUFS - 1)) * P.buf_cols + t * P.n);
-            const int od = step_begin + step;
-            auto row_pos = [&](int a, bool &ok) -> size_t {
-                const int oh = h0 + a;
-                ok = od < P.Do && oh < P.Ho && ow < P.Wo;
-                const int odr = P.swap ? oh : od, ohr = P.swap ? od : oh;                 // real (d, h)
-                return ((size_t)odr * P.Hor + ohr) * P.Wo + ow;
-            };
+            const size_t pos_step = pos0 + (size_t)step * step_stride;
             if (P.out_f32) {
                 // `prob`: one real channel -> fp32 logits; up to four rows (12 single-column loads) per wait
+                float *yo = reinterpret_cast<float *>(y) + (size_t)b * vol_o + pos_step;
                 for (int j0 = 0; j0 < my_rows; j0 += 4) {
                     uint32_t r[4][3];
 #pragma unroll
@@ -353,29 +364,31 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (j0 + j >= my_rows) break;
-                        bool ok;
-                        const size_t pos = row_pos(eg + 2 * (j0 + j), ok);
-                        if (!ok) continue;
+                        const int a = eg + 2 * (j0 + j);
+                        if (!w_ok || h0 + a >= P.Ho) continue;
                         const float acc = (__uint_as_float(r[j][0]) + __uint_as_float(r[j][1])) + __uint_as_float(r[j][2]);
-                        float o = fmaf(acc, s_scale[0], s_shift[0]);
+                        float o = fmaf(acc, sc2[0].x, sh2[0].x);
                         if (P.relu) o = fmaxf(o, 0.f);
-                        reinterpret_cast<float *>(y)[(size_t)b * vol_o + pos] = o;
+                        yo[(size_t)a * row_stride] = o;
                     }
                 }
             } else {
                 auto finish = [&](const uint32_t (&r0)[8], const uint32_t (&r1)[8], const uint32_t (&r2)[8], int a, int n0) {
-                    bool ok;
-                    const size_t pos = row_pos(a, ok);
                     const int cc = ct * P.n + n0;
-                    if (!ok || cc >= P.cout_chunks * 8) return;
-                    const size_t oidx = ((size_t)b * P.cout_chunks + (cc >> 3)) * vol_o + pos;
+                    if (!w_ok || h0 + a >= P.Ho || cc >= P.cout_chunks * 8) return;
+                    const size_t oidx = ((size_t)b * P.cout_chunks + (cc >> 3)) * vol_o + pos_step + (size_t)a * row_stride;
                     uint4 sk = make_uint4(0, 0, 0, 0);
                     if (P.has_skip) sk = __ldg(skip + oidx);
-                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + n0);
-                    const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + n0);
-                    const float4 sa = sc4[0], sb = sc4[1], ha = sh4[0], hb = sh4[1];
-                    const float2 sc2[4] = {{sa.x, sa.y}, {sa.z, sa.w}, {sb.x, sb.y}, {sb.z, sb.w}};
-                    const float2 sh2[4] = {{ha.x, ha.y}, {ha.z, ha.w}, {hb.x, hb.y}, {hb.z, hb.w}};
+                    float2 scl[4], shl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { scl[e] = sc2[e]; shl[e] = sh2[e]; }
+                    if (n0 != 0) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            scl[e] = make_float2(s_scale[n0 + 2 * e], s_scale[n0 + 2 * e + 1]);
+                            shl[e] = make_float2(s_shift[n0 + 2 * e], s_shift[n0 + 2 * e + 1]);
+                        }
+                    }
                     const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
                     uint32_t pk[4];
 #pragma unroll
@@ -383,7 +396,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         float2 v = __fadd2_rn(make_float2(__uint_as_float(r0[2 * e]), __uint_as_float(r0[2 * e + 1])),
                                               make_float2(__uint_as_float(r1[2 * e]), __uint_as_float(r1[2 * e + 1])));
                         v = __fadd2_rn(v, make_float2(__uint_as_float(r2[2 * e]), __uint_as_float(r2[2 * e + 1])));
-                        v = __ffma2_rn(v, sc2[e], sh2[e]);
+                        v = __ffma2_rn(v, scl[e], shl[e]);
                         if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
                         if (P.has_skip) {
                             v.x += __uint_as_float(sv[e] << 16);
@@ -416,6 +429,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             mbar_arrive(tempty + (step & (UM_TBUFS - 1)));         // ... slab `step`'s buffer may be overwritten
             rt.lap(7);
         }
+        rt.flush();
     } else
     if (warp >= 4 && warp < 8) {
         // =========================== producers: global -> shared (cp.async) ===========================
@@ -451,7 +465,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             // moves as ONE bulk copy issued by one lane (lane l of producer warp p owns line p + 4 l); only the out-of-
             // volume parts (halo rows / columns, slabs beyond the step axis) are zero-filled with ordinary stores.
             // Everything but the slab index is hoisted, so an interior slab costs a barrier wait + one copy per lane.
-            RoleTimer rt; rt.start(trace && tid == 128, trace);
+            // (Measured: a UBLKCP costs ~450 clk of its warp whoever issues it; spreading the lines over lanes of four
+            // warps beats one elected lane walking them.  One tensor-map TMA per slab is the next step.)
+            RoleTimer rt; rt.start(trace && tid == 128, trace, 1);
             const int c_lo = m0 == 0 ? 1 : 0;                                  // column c holds w = m0 - 1 + c
             const int c_hi = min(UM_COLS, P.W - m0 + 1);
             const int ln = pwarp + (UM_PROD_THREADS / 32) * lane;
@@ -498,6 +514,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 if (d_ok && my_bytes) bulk_copy_g2s(slab + my_dst_off, my_src + (size_t)d_in * step_stride, my_bytes, full + slot);
                 rt.lap(2);
             }
+            rt.flush();
         } else
         for (int i = 0; i < n_slabs; ++i) {
             const int slot = i % P.ring, q = i / P.ring;
@@ -566,7 +583,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
                 const uint32_t idesc0 = umma_idesc_bf16(128, 0);
                 constexpr uint32_t kDescHi = 8u | (1u << 14);
-                RoleTimer rt; rt.start(trace && lane == 0 && iss == 0, trace);
+                RoleTimer rt; rt.start(trace && lane == 0 && iss == 0, trace, 3);
                 for (int sl = iss; sl < n_slabs; sl += 2) {
                     const int slot = sl % P.ring, buf = sl & (UM_TBUFS - 1), use = sl / UM_TBUFS;
                     mbar_wait(full + slot, (uint32_t)(sl / P.ring) & 1u);
@@ -607,6 +624,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     __syncwarp();
                     rt.lap(5);
                 }
+                rt.flush();
             }
         } else if (iss < P.n_issuers) {
             uint32_t leader;

@@ -15,7 +15,7 @@ from mvs_b200 import synth, ops, _lib
 from prof_conv import LAYERS
 
 NAMES = ["cta_total", "prod_wait_empty", "prod_stage", "iss_wait_full", "iss_wait_tempty", "iss_issue", "epi_wait_tfull",
-         "epi_work", "steps", "prologue"]
+         "epi_work", "-", "prologue"]
 
 
 def main():
@@ -48,13 +48,13 @@ def main():
             torch.cuda.synchronize()
             t = buf.view(a.ctas, 16).cpu().double()
             t = t[t[:, 0] > 0]
-            steps = t[:, 8].mean().item()
+            steps = t[:, 10].mean().item()
             print(f"stage {si + 1} {name} cin={cin} cout={cout} {D}x{H}x{W}: {e0.elapsed_time(e1):.3f} ms, {len(t)} CTAs traced, "
                   f"{steps:.1f} steps/CTA")
             if len(t) == 0:
                 continue
             for k, nm in enumerate(NAMES):
-                if nm == "steps":
+                if nm == "-":
                     continue
                 print(f"    {nm:18s} {t[:, k].mean().item():10.0f} clk/CTA   {t[:, k].mean().item() / steps:8.0f} clk/step")
 
