@@ -54,6 +54,9 @@ constexpr int UM_MAX_OPS = 224;
 constexpr int UM_MAX_ACC = 16;
 constexpr int UM_MAX_KSTEPS = 112;
 constexpr int UM_MAX_RING = 8;
+#ifndef UM_MIN_CTAS
+#define UM_MIN_CTAS 2
+#endif
 constexpr int UM_TBUFS = 4;         // per-slab accumulator buffers of the T-merged mode
 
 enum UmMode { UM_CONV_S1 = 0, UM_CONV_S2 = 1, UM_DECONV_S2 = 2 };
@@ -257,8 +260,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <bool TM>
-__global__ void __launch_bounds__(TM ? UM_THREADS_TM : UM_THREADS)
+// MC = CTAs per SM the register allocator must allow (old modes): 3 for layers that live on occupancy, 2 for the
+// skip layers whose epilogue keeps four rows (TMEM + skip loads) in flight
+template <bool TM, int MC>
+__global__ void __launch_bounds__(TM ? UM_THREADS_TM : UM_THREADS, MC)
 conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__ x, const uint4 *__restrict__ wpk,
                    const float *__restrict__ scale, const float *__restrict__ shift, const uint4 *__restrict__ skip,
                    void *__restrict__ y)
@@ -706,7 +711,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
             const uint32_t tcol0 = lane_base + (uint32_t)(buf * P.acc_cols);
             // affine + ReLU + skip + store of one 8-channel block held in v[0..7]
-            auto store_chunk = [&](const uint32_t (&v)[8], int nloc, size_t oidx) {
+            // (the skip operand is fetched by the caller BEFORE the TMEM wait: issued one at a time next to its use,
+            // every skip load costs a full DRAM round trip of this warp)
+            auto store_chunk = [&](const uint32_t (&v)[8], int nloc, size_t oidx, const uint4 &sk) {
                 const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + nloc);
                 const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + nloc);
                 const float4 sa = sc4[0], sb = sc4[1], ha = sh4[0], hb = sh4[1];
@@ -720,7 +727,6 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     o[e] = t;
                 }
                 if (P.has_skip) {
-                    const uint4 sk = __ldg(skip + oidx);
                     const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -763,19 +769,27 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 }
             } else if (P.cout <= 8) {
                 // one 8-channel block per row: x8 loads, two rows in flight per wait
-                for (int a0 = 0; a0 < P.n_acc; a0 += 2) {
-                    uint32_t r0[8], r1[8];
-                    tmem_ld8_nowait(tcol0 + (uint32_t)(a0 * P.n), r0);
-                    const bool two = a0 + 1 < P.n_acc;
-                    if (two) tmem_ld8_nowait(tcol0 + (uint32_t)((a0 + 1) * P.n), r1);
-                    tmem_wait_ld();
-                    bool ok;
-                    size_t pos = out_pos(a0, ok);
-                    if (ok) store_chunk(r0, 0, (size_t)b * P.cout_chunks * vol_o + pos);
-                    if (two) {
-                        pos = out_pos(a0 + 1, ok);
-                        if (ok) store_chunk(r1, 0, (size_t)b * P.cout_chunks * vol_o + pos);
+                // four rows per batch: positions, skip loads and TMEM loads are issued together, one wait
+                constexpr int EB = MC >= 3 ? 2 : 4;
+                for (int a0 = 0; a0 < P.n_acc; a0 += EB) {
+                    uint32_t r[EB][8];
+                    size_t pos[EB];
+                    bool ok[EB];
+                    uint4 sk[EB];
+#pragma unroll
+                    for (int j = 0; j < EB; ++j) {
+                        ok[j] = false;
+                        sk[j] = make_uint4(0, 0, 0, 0);
+                        if (a0 + j < P.n_acc) {
+                            pos[j] = (size_t)b * P.cout_chunks * vol_o + out_pos(a0 + j, ok[j]);
+                            if (P.has_skip && ok[j]) sk[j] = __ldg(skip + pos[j]);
+                            tmem_ld8_nowait(tcol0 + (uint32_t)((a0 + j) * P.n), r[j]);
+                        }
                     }
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < EB; ++j)
+                        if (ok[j]) store_chunk(r[j], 0, pos[j], sk[j]);
                 }
             } else {
                 for (int a = 0; a < P.n_acc; ++a) {
@@ -783,16 +797,22 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     const size_t pos = out_pos(a, ok);
                     for (int n0 = 0; n0 < P.n; n0 += 16) {
                         uint32_t r[16];
+                        const int c0 = ct * P.n + n0;
+                        const bool live = ok && c0 < P.cout, has_hi = c0 + 8 < P.cout_chunks * 8;
+                        const size_t base = ((size_t)b * P.cout_chunks + (c0 >> 3)) * vol_o + pos;
+                        uint4 sk_lo = make_uint4(0, 0, 0, 0), sk_hi = make_uint4(0, 0, 0, 0);
+                        if (P.has_skip && live) {
+                            sk_lo = __ldg(skip + base);
+                            if (has_hi) sk_hi = __ldg(skip + base + vol_o);
+                        }
                         tmem_ld16_nowait(tcol0 + (uint32_t)(a * P.n + n0), r);
                         tmem_wait_ld();
-                        const int c0 = ct * P.n + n0;
-                        if (!ok || c0 >= P.cout) continue;
+                        if (!live) continue;
                         uint32_t lo[8], hi[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) { lo[e] = r[e]; hi[e] = r[8 + e]; }
-                        const size_t base = ((size_t)b * P.cout_chunks + (c0 >> 3)) * vol_o + pos;
-                        store_chunk(lo, n0, base);
-                        if (c0 + 8 < P.cout_chunks * 8) store_chunk(hi, n0 + 8, base + vol_o);
+                        store_chunk(lo, n0, base, sk_lo);
+                        if (has_hi) store_chunk(hi, n0 + 8, base + vol_o, sk_hi);
                     }
                 }
             }
@@ -1304,14 +1324,17 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     const int step_chunks = cdiv(P.steps, P.steps_per_cta);
     dim3 grid(cdiv(m_ext, 128), (unsigned)(P.row_blocks * step_chunks), B * P.cout_tiles);
     MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "grid too large");
-    cudaError_t e = P.tmerged ? cudaFuncSetAttribute(conv3d_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : cudaFuncSetAttribute(conv3d_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto launch = [&](auto kernel, int threads) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed, scale, shift,
+                                                              (const uint4 *)skip_c8, y);
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    if (P.tmerged) e = launch(conv3d_umma_kernel<true, 1>, UM_THREADS_TM);
+    else if (skip_c8) e = launch(conv3d_umma_kernel<false, 2>, UM_THREADS);
+    else e = launch(conv3d_umma_kernel<false, 3>, UM_THREADS);
     if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    if (P.tmerged)
-        conv3d_umma_kernel<true><<<grid, UM_THREADS_TM, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed,
-                                                                                      scale, shift, (const uint4 *)skip_c8, y);
-    else
-        conv3d_umma_kernel<false><<<grid, UM_THREADS, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed,
-                                                                                    scale, shift, (const uint4 *)skip_c8, y);
     return check_launch("mvs_conv3d_c8_fwd");
 }
