@@ -54,6 +54,7 @@ constexpr int UM_MAX_OPS = 224;
 constexpr int UM_MAX_ACC = 16;
 constexpr int UM_MAX_KSTEPS = 112;
 constexpr int UM_MAX_RING = 8;
+constexpr int UM_MAX_LINES = 288;   // staged lines per slab (rows x channel blocks x arrays)
 #ifndef UM_MIN_CTAS
 #define UM_MIN_CTAS 2
 #endif
@@ -279,6 +280,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + UM_TBUFS);
     float *s_scale = reinterpret_cast<float *>(tmem_slot + 4);       // [n] folded-BN scale of this Cout tile (0 for padding)
     float *s_shift = s_scale + 32;                                   // [n] shift
+    // [lines] per staged line: vector offset of (line, step 0, w 0) in x, or ~0 for a line outside the volume
+    unsigned long long *s_line = reinterpret_cast<unsigned long long *>(s_shift + 32);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch, issuer id)
@@ -308,6 +311,20 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int c = ct * P.n + tid;
         s_scale[tid] = c < P.cout ? (scale ? __ldg(scale + c) : 1.f) : 0.f;
         s_shift[tid] = c < P.cout ? (shift ? __ldg(shift + c) : 0.f) : 0.f;
+    }
+    if (!TM) {
+        // producer line table: everything about a staged line that does not depend on the slab
+        const int lines = P.rh * P.cin_chunks * P.arr;
+        const size_t plane_in = (size_t)P.Hr * P.W;
+        for (int ln = tid; ln < lines; ln += UM_THREADS) {
+            const int chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
+            const int h_in = P.h_mul * h0 + P.h_base + r;
+            unsigned long long v = ~0ull;
+            if (h_in >= 0 && h_in < P.H)
+                v = (unsigned long long)((((size_t)b * P.cin_chunks + chunk) * P.Dr + (P.swap ? h_in : 0)) * plane_in +
+                                         (P.swap ? (size_t)0 : (size_t)h_in * P.W));
+            s_line[ln] = v;
+        }
     }
     fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
@@ -442,29 +459,16 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int lines = P.rh * P.cin_chunks * P.arr;                // lines of UM_COLS 16-byte vectors per slab
         const size_t plane_in = (size_t)P.Hr * P.W;
         int pending = -1;              // slab staged (cp.async committed) but not yet published
-        auto stage_slab = [&](int i, int slot) {
-            const int d_in = P.d_base + P.d_mul * step_begin + i;
-            const bool d_ok = d_in >= 0 && d_in < P.D;
-            uint4 *slab = sa + (size_t)slot * P.slab_units;
-            for (int ln = pwarp; ln < lines; ln += UM_PROD_THREADS / 32) {
-                const int a = ln % P.arr, chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
-                const int h_in = P.h_mul * h0 + P.h_base + r;
-                const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
-                const int dr = row_ok ? (P.swap ? h_in : d_in) : 0, hr = row_ok ? (P.swap ? d_in : h_in) : 0;   // real (d, h)
-                const uint4 *src = x + (((size_t)b * P.cin_chunks + chunk) * P.Dr + dr) * plane_in + (size_t)hr * P.W;
-                uint4 *dst = slab + (size_t)ln * UM_COLS;
-                const int wb = P.w_step * m0 + P.w_base[a];
+        // per-thread column offsets of the (up to two) staged arrays and the per-slab stride, hoisted out of the loops
+        int wofs[2][(UM_COLS + 31) / 32];
 #pragma unroll
-                for (int cc = 0; cc < (UM_COLS + 31) / 32; ++cc) {
-                    const int c = cc * 32 + lane;
-                    if (c < UM_COLS) {
-                        const int w_in = P.w_step * c + wb;
-                        const bool ok = row_ok && w_in >= 0 && w_in < P.W;
-                        cp_async16(dst + c, src + (ok ? w_in : 0), ok ? 16u : 0u);
-                    }
-                }
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int cc = 0; cc < (UM_COLS + 31) / 32; ++cc) {
+                const int w_in = P.w_step * (cc * 32 + lane) + P.w_step * m0 + P.w_base[a];
+                wofs[a][cc] = (w_in >= 0 && w_in < P.W) ? w_in : -1;
             }
-        };
+        const size_t slab_stride = P.swap ? (size_t)P.W : plane_in;
         if (TM) {
             // A staged line (one row of one channel block, 132 consecutive voxels) is contiguous in global memory, so it
             // moves as ONE bulk copy issued by one lane (lane l of producer warp p owns line p + 4 l); only the out-of-
@@ -537,20 +541,19 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const int d_in = P.d_base + P.d_mul * step_begin + i;
             const bool d_ok = d_in >= 0 && d_in < P.D;
             uint4 *slab = sa + (size_t)slot * P.slab_units;
+            const uint4 *xs = x + (size_t)(d_ok ? d_in : 0) * slab_stride;
             for (int ln = pwarp; ln < lines; ln += UM_PROD_THREADS / 32) {
-                const int a = ln % P.arr, chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
-                const int h_in = P.h_mul * h0 + P.h_base + r;
-                const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
-                const int dr = row_ok ? (P.swap ? h_in : d_in) : 0, hr = row_ok ? (P.swap ? d_in : h_in) : 0;   // real (d, h)
-                const uint4 *src = x + (((size_t)b * P.cin_chunks + chunk) * P.Dr + dr) * plane_in + (size_t)hr * P.W;
+                const unsigned long long lb = s_line[ln];
+                const bool row_ok = d_ok && lb != ~0ull;
+                const uint4 *src = xs + (row_ok ? (size_t)lb : 0);
                 uint4 *dst = slab + (size_t)ln * UM_COLS;
-                const int wb = P.w_step * m0 + P.w_base[a];
+                const int a = P.arr == 2 ? (ln & 1) : 0;
 #pragma unroll
                 for (int cc = 0; cc < (UM_COLS + 31) / 32; ++cc) {
                     const int c = cc * 32 + lane;
                     if (c < UM_COLS) {
-                        const int w_in = P.w_step * c + wb;
-                        const bool ok = row_ok && w_in >= 0 && w_in < P.W;
+                        const int w_in = a ? wofs[1][cc] : wofs[0][cc];     // -1: outside the row (static indices: registers)
+                        const bool ok = row_ok && w_in >= 0;
                         cp_async16(dst + c, src + (ok ? w_in : 0), ok ? 16u : 0u);
                     }
                 }
@@ -1001,7 +1004,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
 
 static size_t plan_smem_bytes(int weight_units, int ring, int slab_units)
 {
-    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 2 * UM_TBUFS) * 8 + 16 + 64 * 4;
+    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 2 * UM_TBUFS) * 8 + 16 + 64 * 4 + UM_MAX_LINES * 8;
 }
 
 static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
