@@ -43,6 +43,7 @@ extern "C" {
 #define MVS_INPUT_IS_PROB 32    /* softargmin: input already soft-maxed (depth_regression(p, d)) */
 #define MVS_BLEND_BF16 64       /* C8 builder: bilinear blend in packed bf16x2 (sums / variance stay fp32) */
 #define MVS_FAST_COORDS 128     /* mvs_warp_taps: probe the C8 builder's division-free-call tap arithmetic */
+#define MVS_FEAT_F16 256        /* C8 builder: feature maps are fp16 C8 (mvs_pack_c8h); blend in packed fp16  */
 
 /* depth_mode */
 #define MVS_DEPTH_PLANE 0       /* depth [B,D]       MVSNet/models/module.py:46                   */
@@ -51,6 +52,7 @@ extern "C" {
 /* dtype */
 #define MVS_F32 0
 #define MVS_BF16 1
+#define MVS_F16 2
 
 #define MVS_MAX_SRC 8           /* source views the fused builder takes in one launch            */
 
@@ -112,6 +114,10 @@ int mvs_warp_variance_c8_fwd(const void *ref_c8, const void *const *srcs_c8_host
  * multiple of 8 on pack; unpack drops the padding. */
 int mvs_pack_c8(const void *src, int src_dtype, void *dst_c8, int B, int C, int64_t inner, void *stream);
 int mvs_unpack_c8(const void *src_c8, void *dst, int dst_dtype, int B, int C, int64_t inner, void *stream);
+/* Same layout with fp16 elements ("C8H"), the feature-map format of the fast builder (MVS_FEAT_F16): 11-bit
+ * significands instead of bf16's 8, and the bilinear blend runs on HFMA2 without per-tap unpacking.  Values are
+ * clamped to +-65504 (fp16 max) instead of overflowing to infinity. */
+int mvs_pack_c8h(const void *src, int src_dtype, void *dst_c8h, int B, int C, int64_t inner, void *stream);
 
 /* ---- a3: 3x3x3 convolution + folded BatchNorm + ReLU + skip ------------------------------------
  * Replaces ConvBnReLU3D / Conv3d / Deconv3d blocks and the skip adds of CostRegNet.forward:

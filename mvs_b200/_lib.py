@@ -19,6 +19,7 @@ CLAMP_INDEX = 16
 INPUT_IS_PROB = 32
 BLEND_BF16 = 64
 FAST_COORDS = 128
+FEAT_F16 = 256
 DEPTH_PLANE = 0
 DEPTH_PIXEL = 1
 F32 = 0
@@ -41,6 +42,7 @@ SIGNATURES = {
     "mvs_warp_variance_c8_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp] + [_i] * 6 + [_vp]),
     "mvs_pack_c8": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
     "mvs_unpack_c8": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp]),
+    "mvs_pack_c8h": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
     "mvs_conv3d_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
     "mvs_conv3d_c8_packed_weight_bytes": (_i64, [_i] * 4),
     "mvs_conv3d_c8_pack_weights": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),

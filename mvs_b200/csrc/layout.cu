@@ -34,6 +34,28 @@ pack_c8_kernel(const T *__restrict__ src, uint4 *__restrict__ dst, int C, long l
 
 template <typename T>
 __global__ void __launch_bounds__(256)
+pack_c8h_kernel(const T *__restrict__ src, uint4 *__restrict__ dst, int C, long long inner)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= inner) return;
+    const int cb = blockIdx.y, b = blockIdx.z, CB = gridDim.y;
+    const T *s = src + ((size_t)b * C + (size_t)cb * 8) * inner + i;
+    __half2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c0 = cb * 8 + 2 * k;
+        float a = c0 < C ? to_f32<T>(s[(size_t)(2 * k) * inner]) : 0.f;
+        float bb = c0 + 1 < C ? to_f32<T>(s[(size_t)(2 * k + 1) * inner]) : 0.f;
+        // saturate instead of overflowing to inf; fminf / fmaxf drop NaN, so NaN is passed through explicitly
+        a = a != a ? a : fminf(fmaxf(a, -65504.f), 65504.f);
+        bb = bb != bb ? bb : fminf(fmaxf(bb, -65504.f), 65504.f);
+        v[k] = __floats2half2_rn(a, bb);
+    }
+    dst[((size_t)b * CB + cb) * inner + i] = *reinterpret_cast<uint4 *>(v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
 unpack_c8_kernel(const uint4 *__restrict__ src, T *__restrict__ dst, int C, long long inner)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,6 +85,20 @@ extern "C" int mvs_pack_c8(const void *src, int src_dtype, void *dst_c8, int B, 
     else
         pack_c8_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, (uint4 *)dst_c8, C, inner);
     return check_launch("mvs_pack_c8");
+}
+
+extern "C" int mvs_pack_c8h(const void *src, int src_dtype, void *dst_c8h, int B, int C, int64_t inner, void *stream)
+{
+    if (B == 0 || C == 0 || inner == 0) return MVS_OK;
+    MVS_REQUIRE(B > 0 && C > 0 && inner > 0 && B <= 65535, "bad extents");
+    MVS_REQUIRE(src && dst_c8h, "null pointer");
+    MVS_REQUIRE(src_dtype == MVS_F32 || src_dtype == MVS_BF16, "bad dtype");
+    dim3 grid(cdiv(inner, 256), cdiv(C, 8), B);
+    if (src_dtype == MVS_F32)
+        pack_c8h_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)src, (uint4 *)dst_c8h, C, inner);
+    else
+        pack_c8h_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, (uint4 *)dst_c8h, C, inner);
+    return check_launch("mvs_pack_c8h");
 }
 
 extern "C" int mvs_unpack_c8(const void *src_c8, void *dst, int dst_dtype, int B, int C, int64_t inner, void *stream)

@@ -262,7 +262,7 @@ def build_cost_volume_c8(ref_fea, src_feas: Sequence[torch.Tensor], ref_proj, sr
     """Fast-path builder: feature maps (NCHW fp32/bf16, or already C8 bf16 [B,CB,h,w,8]) -> C8 bf16
     variance volume [B,CB,D,h,w,8] for the tensor-core CostRegNet."""
     rots, transs = zip(*(ops.relative_pose(sp, ref_proj) for sp in src_projs))
-    as_c8 = lambda t: t if (t.dim() == 5 and t.dtype == torch.bfloat16 and t.shape[-1] == 8) else ops.pack_c8(t)
+    as_c8 = lambda t: t if (t.dim() == 5 and ops.is_c8(t)) else ops.pack_c8(t, ops.FAST_FEATURE_DTYPE)
     return ops.cost_volume_c8(as_c8(ref_fea), [as_c8(s) for s in src_feas], list(rots), list(transs), depth_values,
                               flags)
 
@@ -276,7 +276,7 @@ def stage_forward(features, rot, trans, depth_values, cost_regularization, clamp
     rots = [rot[:, i].contiguous() for i in range(nsrc)]
     transs = [trans[:, i].contiguous() for i in range(nsrc)]
     if _is_fast(cost_regularization):
-        as_c8 = lambda t: t if (t.dim() == 5 and t.dtype == torch.bfloat16 and t.shape[-1] == 8) else ops.pack_c8(t)
+        as_c8 = lambda t: t if (t.dim() == 5 and ops.is_c8(t)) else ops.pack_c8(t, ops.FAST_FEATURE_DTYPE)
         var = ops.cost_volume_c8(as_c8(features[0]), [as_c8(f) for f in features[1:]], rots, transs, depth_values, flags)
     else:
         var = ops.cost_volume(features[0], list(features[1:]), rots, transs, depth_values, flags)

@@ -232,9 +232,12 @@ def cost_volume(ref_fea, src_feas, rots, transs, depth_values, flags=0):
     return _CostVolumeFn.apply(ref_fea, rot, trans, depth_values, flags, *src_feas)
 
 
-def pack_c8(x: torch.Tensor) -> torch.Tensor:
-    """NC(D)HW fp32/bf16 -> C8 bf16 [B, ceil(C/8), *spatial, 8]."""
+def pack_c8(x: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """NC(D)HW fp32/bf16 -> C8 [B, ceil(C/8), *spatial, 8] in `dtype`: bf16 (activations of the conv stack) or
+    fp16 ("C8H", the feature-map format of the fast builder; values saturate at +-65504)."""
     _dev(x)
+    if dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("pack_c8: dtype must be torch.bfloat16 or torch.float16")
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     x = x.contiguous()
@@ -243,11 +246,20 @@ def pack_c8(x: torch.Tensor) -> torch.Tensor:
     inner = 1
     for s in spatial:
         inner *= s
-    out = torch.empty((B, (Cc + 7) // 8, *spatial, 8), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((B, (Cc + 7) // 8, *spatial, 8), dtype=dtype, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib().mvs_pack_c8(_p(x), L.F32 if x.dtype == torch.float32 else L.BF16, _p(out), B, Cc, inner,
-                                _stream()), "mvs_pack_c8")
+        fn = lib().mvs_pack_c8 if dtype == torch.bfloat16 else lib().mvs_pack_c8h
+        check(fn(_p(x), L.F32 if x.dtype == torch.float32 else L.BF16, _p(out), B, Cc, inner, _stream()), "mvs_pack_c8")
     return out
+
+
+def is_c8(t: torch.Tensor) -> bool:
+    """A packed C8 / C8H feature map or volume (trailing dimension of 8 sixteen-bit elements)."""
+    return t.dtype in (torch.bfloat16, torch.float16) and t.dim() >= 4 and t.shape[-1] == 8
+
+
+# feature-map format the fast path packs NCHW features into (MVS_C8_FEATURES=bf16 restores bf16 features + fp32 blend)
+FAST_FEATURE_DTYPE = torch.bfloat16 if __import__("os").environ.get("MVS_C8_FEATURES", "f16") == "bf16" else torch.float16
 
 
 def unpack_c8(x_c8: torch.Tensor, channels: int, dtype=torch.float32) -> torch.Tensor:
@@ -267,7 +279,12 @@ def unpack_c8(x_c8: torch.Tensor, channels: int, dtype=torch.float32) -> torch.T
 
 
 def cost_volume_c8(ref_c8, srcs_c8, rots, transs, depth_values, flags=0):
-    """Fused builder, fast path: C8 bf16 feature maps [B,CB,H,W,8] -> C8 bf16 volume [B,CB,D,H,W,8]."""
+    """Fused builder, fast path: C8 feature maps [B,CB,H,W,8] (all bf16, or all fp16 = C8H) -> C8 bf16 volume
+    [B,CB,D,H,W,8]."""
+    if any(t.dtype != ref_c8.dtype for t in srcs_c8) or ref_c8.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("cost_volume_c8: feature maps must all be bf16 C8 or all be fp16 C8H")
+    if ref_c8.dtype == torch.float16:
+        flags |= L.FEAT_F16
     depth_values = _f32c(depth_values)
     rot, trans = _stack_pose(rots, transs)
     _dev(ref_c8, rot, trans, depth_values, *srcs_c8)

@@ -434,6 +434,39 @@ def test_cost_volume_c8_bf16_blend_vs_oracle(C, pixel, nsrc):
     print("bf16-blend max abs err", np.abs(out - ref).max(), "mean abs err", np.abs(out - ref).mean())
 
 
+@pytest.mark.parametrize("C,pixel,nsrc", [(32, False, 4), (16, True, 4), (8, True, 2), (8, False, 6)])
+def test_cost_volume_c8h_fp16_features_vs_oracle(C, pixel, nsrc):
+    """MVS_FEAT_F16 (the fast path's default feature format): fp16 C8H features, bilinear blend in packed fp16
+    (11-bit significands), sums over views / variance in fp32, bf16 volume out.  Against the oracle fed the SAME
+    fp16-rounded features the tolerance is the bf16 rounding of the stored result plus the four fp16 roundings of
+    the blend: 2^-7 relative + 4e-3 absolute (features ~N(0,1)) -- the same bound as the fp32-blend bf16 path."""
+    from mvs_b200 import ops
+    v = cases.volume_case(n_views=nsrc + 1, C=C, H=21, W=40, D=6, seed=30 + C, per_pixel=pixel)
+    feats = torch.from_numpy(v["feats"]).half().float().numpy()
+    p = torch.from_numpy(v["proj"])
+    prod = torch.stack([p[:, i] @ torch.inverse(p[:, 0]) for i in range(1, nsrc + 1)], 1).numpy()
+    rot, tr = rt(prod)
+    ref = O.cost_volume(feats[0], feats[1:], rot, tr, v["depth"])
+    rots = [cu(rot[:, i].reshape(-1, 9)) for i in range(nsrc)]
+    trs = [cu(tr[:, i]) for i in range(nsrc)]
+    packed = [ops.pack_c8(cu(f), torch.float16) for f in feats]
+    assert packed[0].dtype == torch.float16
+    # the C8H pack is exact on fp16-representable inputs: [B,CB,H,W,8] -> NCHW
+    back = packed[0].permute(0, 1, 4, 2, 3).reshape(feats[0].shape[0], -1, *feats[0].shape[2:])[:, :C].float()
+    assert np.array_equal(npy(back), feats[0])
+    vol = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, cu(v["depth"]))
+    out = npy(ops.unpack_c8(vol, C))
+    np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=4e-3)
+    print("fp16-feature path max abs err", np.abs(out - ref).max(), "mean abs err", np.abs(out - ref).mean())
+
+
+def test_pack_c8h_saturates():
+    from mvs_b200 import ops
+    x = torch.tensor([1e6, -1e6, 3.0, float("nan")], device=DEV).reshape(1, 4, 1, 1)
+    p = ops.pack_c8(x, torch.float16).flatten()[:4].float()
+    assert p[0] == 65504 and p[1] == -65504 and p[2] == 3 and torch.isnan(p[3])
+
+
 def test_cvp_pyramid_golden():
     """CVP-MVSNet network.forward (nscale=2, test mode) from feature pyramids: coarse sweep + one refine
     level incl. calDepthHypo's statistical interval, vs the reference's outputs."""

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attribute the warp-state samples of a conv3d_umma_kernel capture to pipeline roles / barrier waits.
     python tools/ncu_roles.py gpurun_out/x.ncu-rep
-Barrier offsets in the CTA's barrier block: +0x00 full[], +0x30 empty[], +0x60 tfull[], +0x70 tempty[]."""
+Barrier offsets in the CTA's barrier block: +0x00 full[8], +0x40 empty[8], +0x80 tfull[4], +0xa0 tempty[4]."""
 import collections
 import csv
 import io
@@ -16,15 +16,15 @@ h = [i for i, r in enumerate(rows) if "Source" in r][0]
 hdr = rows[h]; cs = hdr.index("Source"); samp = hdr.index("# Samples")
 body = rows[h + 1:]
 tot = sum(float(r[samp] or 0) for r in body)
-names = {0x00: "wait full   (issuer  <- loads)", 0x30: "wait empty  (producer <- free slot)",
-         0x60: "wait tfull  (epilogue <- MMAs)", 0x70: "wait tempty (issuer  <- epilogue)"}
+names = {0x00: "wait full   (issuer  <- loads)", 0x40: "wait empty  (producer <- free slot)",
+         0x80: "wait tfull  (epilogue <- MMAs)", 0xa0: "wait tempty (issuer  <- epilogue)"}
 agg = collections.Counter(); last = None
 for r in body:
     s = r[cs]; n = float(r[samp] or 0)
     m = re.search(r"TRYWAIT[^\[]*\[[^\]]*?(?:\+0x([0-9a-f]+))?\]", s)
     if m:
         off = int(m.group(1) or "0", 16)
-        key = 0x70 if off >= 0x70 else 0x60 if off >= 0x60 else 0x30 if off >= 0x30 else 0
+        key = 0xa0 if off >= 0xa0 else 0x80 if off >= 0x80 else 0x40 if off >= 0x40 else 0
         last = names[key]; agg[last] += n; continue
     if last and ("BRA" in s or "YIELD" in s or "NOP" in s):
         agg[last] += n; continue

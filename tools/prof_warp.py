@@ -52,10 +52,10 @@ def main():
         _, _, mask, _ = ops.warp_taps(rots[0], trs[0], depth, h, w, want_ixy=False)
         inb = float((mask == 15).float().mean())
         del mask
-        modes = ["c8", "c8b", "strict"] if a.mode == "both" else a.mode.split(",")
+        modes = ["c8h", "c8", "c8b", "strict"] if a.mode == "both" else a.mode.split(",")
         for mode in modes:
-            if mode in ("c8", "c8b"):
-                packed = [ops.pack_c8(f) for f in feats]
+            if mode in ("c8", "c8b", "c8h"):
+                packed = [ops.pack_c8(f, torch.float16 if mode == "c8h" else torch.bfloat16) for f in feats]
                 fl = 64 if mode == "c8b" else 0        # MVS_BLEND_BF16
                 fn = lambda: ops.cost_volume_c8(packed[0], packed[1:], rots, trs, depth, fl)
                 s = 2
