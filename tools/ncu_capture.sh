@@ -5,8 +5,8 @@ tag=${1:-r1b}
 mkdir -p gpurun_out
 NCU="ncu --set full --clock-control none --import-source on -f"
 for st in 1 2 3; do
-  $NCU -k regex:warp_variance_c8 --launch-skip 3 -c 1 -o gpurun_out/${tag}_warp_c8_s${st} \
-      python tools/prof_warp.py --mode c8 --stages $st --reps 1 > gpurun_out/${tag}_warp_c8_s${st}.log 2>&1
+  $NCU -k regex:warp_variance_c8 --launch-skip 3 -c 1 -o gpurun_out/${tag}_warp_c8h_s${st} \
+      python tools/prof_warp.py --mode c8h --stages $st --reps 1 > gpurun_out/${tag}_warp_c8h_s${st}.log 2>&1
 done
 for spec in "conv0 1" "conv0 3" "prob 3" "conv11 3" "conv1 3"; do
   set -- $spec
