@@ -238,14 +238,62 @@ def main_ours(args):
             return cascade.cascade_hot_path(fs, projs, dv, regs, ndepths=NDEPTHS, img_hw=IMG_HW, depth_min=dmin,
                                             depth_max=dmax)
 
-    # e2e: every step copies ITS inputs from pinned host memory and reads its result back.  The copy of
+    def timed(fn, k, tail=None):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        if tail is not None:
+            tail()                                       # e.g. make the timing stream wait for side-stream work
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- pass 1 (eager launches, per-kernel CUDA events): roofline of the fused builder + the eager step time ----
+    for _ in range(max(args.warmup, 3)):
+        step(feats)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ops.KERNEL_TIMERS = {}
+    ms_eager = timed(lambda: step(feats), args.steps)
+    timers, ops.KERNEL_TIMERS = ops.KERNEL_TIMERS, None
+    launches_per_step = (_lib.launch_count() - n0) // args.steps
+
+    # ---- pass 2 (the deployment form): the same step captured once in a CUDA graph (mvs_b200.GraphedStep) and
+    # replayed -- ~85 launches per ref view cost more host time than GPU time once issued one by one from Python ----
+    use_graph = not args.no_graph
+    if use_graph:
+        from mvs_b200.graph import GraphedStep
+        g_res = GraphedStep(lambda: step(feats))
+        for _ in range(2):
+            g_res()
+        ms = timed(g_res, args.steps)
+    else:
+        ms = ms_eager
+    clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
+
+    # ---- e2e: every step copies ITS inputs from pinned host memory and reads its result back.  The copy of
     # step i+1 runs on a copy stream into the other half of a double buffer while step i computes --
     # how a feeder thread would drive the C-ABI; nothing is reused across steps.
     copy_stream = torch.cuda.Stream(device=dev)
     dbuf = [[{k: torch.empty_like(t, device=dev) for k, t in f.items()} for f in pinned] for _ in range(2)]
     ev_ready = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
+    d2h_stream = torch.cuda.Stream(device=dev)
+    ev_d2h = [torch.cuda.Event() for _ in range(2)]
     e2e_i = [0]
+    if use_graph:
+        g_e2e = [GraphedStep(lambda j=j: step(dbuf[j])) for j in range(2)]      # one captured step per buffer half
+        run_half = lambda j: g_e2e[j]()
+    else:
+        run_half = lambda j: step(dbuf[j])
 
     def step_e2e():
         i = e2e_i[0]; e2e_i[0] += 1
@@ -259,38 +307,32 @@ def main_ours(args):
                     fd[k].copy_(t, non_blocking=True)
             ev_ready[j].record(copy_stream)
         cur.wait_event(ev_ready[j])
-        out = step(dbuf[j])
+        if i >= 2:
+            cur.wait_event(ev_d2h[j])                    # the read-back of this half's previous result has finished
+        out = run_half(j)
         ev_free[j].record(cur)
-        host_out[0].copy_(out["depth"], non_blocking=True)
-        host_out[1].copy_(out["photometric_confidence"], non_blocking=True)
+        # result read-back on its own stream: PCIe is full duplex, so it overlaps the next step's compute and input copy
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ev_free[j])
+            host_out[0].copy_(out["depth"], non_blocking=True)
+            host_out[1].copy_(out["photometric_confidence"], non_blocking=True)
+            ev_d2h[j].record(d2h_stream)
 
-    def timed(fn, k):
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(k):
-            fn()
-        b.record()
-        barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    for _ in range(max(args.warmup, 3)):
-        step(feats)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    n0 = _lib.launch_count()
-    ops.KERNEL_TIMERS = {}
-    ms = timed(lambda: step(feats), args.steps)
-    timers, ops.KERNEL_TIMERS = ops.KERNEL_TIMERS, None
-    launches = _lib.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    def e2e_tail():                                      # the timed region ends when the LAST result has landed on the host
+        cur = torch.cuda.current_stream()
+        for j in range(2):
+            cur.wait_event(ev_d2h[j])
+    ms_e2e = timed(step_e2e, args.steps, e2e_tail)
+
+    # the same host->device copies alone (no compute): shows how much of the e2e step is the PCIe transfer
+    def h2d_only():
+        for fd, fh in zip(dbuf[0], pinned):
+            for k, t in fh.items():
+                fd[k].copy_(t, non_blocking=True)
+    h2d_only()
+    ms_h2d = timed(h2d_only, args.steps)
 
     # roofline of the fused warp+variance kernel from the events recorded inside the timed region
     ev = timers.get("warp_variance", [])
@@ -324,18 +366,24 @@ def main_ours(args):
         "metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "strict" else "bf16",
-        "data": "synthetic",
+        "data": "synthetic", "eager_ms_per_step": ms_eager / args.steps,
+        "launch": ("CUDA graph replay of the captured step (mvs_b200.GraphedStep); eager_ms_per_step = the same step issued "
+                   "launch by launch from Python, the pass the per-kernel events of `roofline` come from") if use_graph
+                  else "eager launches",
         "config": {"workload": "cfg3: CasMVSNet 3-stage hot path 1600x1184 N=5 D=(48,32,8), 1 ref view per GPU per step",
                    "mode": args.mode, "l2": "inputs+intermediates per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                   "features": ("bf16" if args.mode == "fast" else "fp32") + " NCHW feature maps (packed to C8 bf16 inside the step in fast mode)"},
+                   "features": ("bf16" if args.mode == "fast" else "fp32") + " NCHW feature maps (packed to fp16 C8H inside the step in fast mode)"},
         "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                "h2d_only_ms_per_step": ms_h2d / args.steps,
+                "note": "input copy overlaps the previous step's compute on a copy stream; the step is PCIe-bound when "
+                        "h2d_only_ms_per_step ~ ms_per_step"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "warp_variance (fused homography warp + variance, 3 launches/step)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                      "avg_launch_ms": kernel_ms / max(n_launch, 1), "launches_timed": n_launch,
-                     "share_of_step": kernel_ms / ms if ms > 0 else None},
+                     "share_of_step": kernel_ms / ms_eager if ms_eager > 0 else None},
         "clocks": clocks,
     }
     if cpu is not None:
@@ -357,6 +405,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fast", choices=["strict", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches only (no CUDA graph replay)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-cuDNN side measurement")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -17,7 +17,7 @@ _LAZY = {
     "CostRegNet": "modules", "CostRegNetMVSNet": "modules", "CostRegNetCas": "modules", "CostRegNetCVP": "modules",
     "DepthNet": "modules", "build_cost_volume": "modules", "proj_cost": "modules", "mvsnet_hot_path": "modules",
     "ConvBnReLU3D": "modules", "Conv3d": "modules", "Deconv3d": "modules",
-    "cascade_hot_path": "cascade", "patch_reference": "patch",
+    "cascade_hot_path": "cascade", "patch_reference": "patch", "graph": "graph", "GraphedStep": "graph",
 }
 
 

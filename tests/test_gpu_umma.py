@@ -156,3 +156,39 @@ def test_cfg5_builder_seven_views_full_size():
     strict = ops.cost_volume(feats[0], feats[1:], rots, trs, depth)
     fast = ops.unpack_c8(ops.cost_volume_c8(ops.pack_c8(feats[0]), [ops.pack_c8(f) for f in feats[1:]], rots, trs, depth), C)
     assert ((fast - strict).abs() <= strict.abs() * 2 ** -7 + 2e-3).all()
+
+
+def test_graphed_step_replays_the_cascade():
+    """mvs_b200.GraphedStep: the whole 3-stage fast cascade captured in one CUDA graph replays bit-identically to the
+    eager launches, also after the static inputs were updated in place (the C-ABI only enqueues on the given stream)."""
+    from mvs_b200 import modules, cascade
+    from mvs_b200.graph import GraphedStep
+    k = cases.cascade_case()
+    regs = []
+    for i, cin in enumerate((32, 16, 8)):
+        net = modules.CostRegNet(cin, 8, mode="fast")
+        net.load_state_dict({kk: torch.from_numpy(np.asarray(v)) for kk, v in cases.costreg_state("cas", cin=cin, seed=14 + i).items()}, strict=True)
+        regs.append(net.to(DEV).eval())
+    n_views = k["feats"]["stage1"].shape[0]
+    feats = [{s: cu(k["feats"][s][v]) for s in k["feats"]} for v in range(n_views)]
+    projs = {s: cu(p) for s, p in k["projs"].items()}
+    dv = cu(k["depth_values"])
+    dmin, dmax = float(k["depth_values"][0, 0]), float(k["depth_values"][0, -1])
+    run = lambda: cascade.cascade_hot_path(feats, projs, dv, regs, ndepths=k["ndepths"], img_hw=(k["H"], k["W"]),
+                                           depth_min=dmin, depth_max=dmax)
+    with torch.no_grad():
+        eager = {s: run()[s]["depth"].clone() for s in ("stage1", "stage2", "stage3")}
+        g = GraphedStep(run)
+        out = g()
+        torch.cuda.synchronize()
+        for s in eager:
+            assert torch.equal(out[s]["depth"], eager[s]), s
+        # new inputs, in place: replay must follow them
+        for f in feats:
+            for s in f:
+                f[s].mul_(0.5)
+        eager2 = run()["stage3"]["depth"].clone()
+        out2 = g()
+        torch.cuda.synchronize()
+        assert torch.equal(out2["stage3"]["depth"], eager2)
+        assert not torch.equal(eager2, eager["stage3"])
