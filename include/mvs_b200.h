@@ -174,6 +174,25 @@ int mvs_depth_range_samples(const float *cur, double interval, int ndepth, float
 int mvs_cas_hypotheses(const float *prev_depth, int hp, int wp, int H, int W, int h, int w, int ndepth,
                        double interval, float *out, int B, void *stream);
 
+/* ---- f4: geometric-consistency filter of estimated depth maps (the step after the path) ------
+ * Replaces reproject_with_depth + check_geometric_consistency (MVSNet/eval.py:138-208, CasMVSNet/test.py:237-294)
+ * and the per-reference-view fusion loop of filter_depth (MVSNet/eval.py:240-263).  Depth / confidence maps fp32 [H,W]
+ * (device).  `cam` (device, float64) holds, per (ref, src) pair, the 60 doubles the reference derives with
+ * np.linalg.inv / np.matmul:  inv(K_ref)[9] | (E_src @ inv(E_ref))[:3][12] | K_src[9] | inv(K_src)[9] |
+ * (E_ref @ inv(E_src))[:3][12] | K_ref[9].  float64 arithmetic where the reference's NumPy is float64, cv2.remap's
+ * fixed-point bilinear sampling (1/32 px, constant border 0) reproduced exactly.  Any output pointer may be NULL.
+ * mvs_geo_consistency: one pair; depth_reproj is zeroed where the mask fails iff apply_mask (check_* vs reproject_*).
+ * mvs_geo_fuse: all sources of one reference view in one pass: geo_sum int32 = number of consistent sources,
+ * depth_avg float64 = (sum of masked reprojected depths + ref depth) / (geo_sum + 1), final_mask = (conf > conf_thresh)
+ * & (geo_sum >= min_views); optional per-source masks [nsrc,H,W] u8 and masked reprojected depths [nsrc,H,W]. */
+int mvs_geo_consistency(const float *depth_ref, const float *depth_src, const double *cam, uint8_t *mask,
+                        float *depth_reproj, float *x_src, float *y_src, float *x_rep, float *y_rep, int H, int W,
+                        double dist_thresh, float rel_thresh, int apply_mask, void *stream);
+int mvs_geo_fuse(const float *depth_ref, const float *conf, const void *const *depth_srcs_host, int nsrc,
+                 const double *cams, int32_t *geo_sum, double *depth_avg, uint8_t *final_mask, uint8_t *geo_masks,
+                 float *depth_reproj, int H, int W, double dist_thresh, float rel_thresh, float conf_thresh,
+                 int min_views, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

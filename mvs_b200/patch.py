@@ -31,6 +31,24 @@ _BY_FAMILY = {
 }
 
 
+def patch_fusion(*mods) -> dict:
+    """Rebind `reproject_with_depth` / `check_geometric_consistency` (MVSNet/eval.py:138-208, CasMVSNet/test.py:237-294)
+    in the given modules -- or, with no arguments, in every loaded module that defines both (eval.py / test.py run as
+    scripts define them in `__main__`).  The replacements take and return NumPy arrays like the originals."""
+    from . import fusion
+    if not mods:
+        mods = tuple(m for m in list(sys.modules.values())
+                     if m is not None and callable(getattr(m, "reproject_with_depth", None)) and
+                     callable(getattr(m, "check_geometric_consistency", None)) and m is not fusion
+                     and not getattr(m, "__name__", "").startswith("mvs_b200"))
+    done = {}
+    for m in mods:
+        m.reproject_with_depth = fusion.reproject_with_depth
+        m.check_geometric_consistency = fusion.check_geometric_consistency
+        done[m.__name__] = ["reproject_with_depth", "check_geometric_consistency"]
+    return done
+
+
 def _family_of(mod: types.ModuleType) -> str:
     names = set(vars(mod))
     if "proj_cost" in names or "depth_regression_refine" in names or "network" in names:

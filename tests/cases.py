@@ -121,3 +121,40 @@ def logits_case(B=2, D=12, H=10, W=14, seed=7, per_pixel=False):
     logits = (3.0 * rng.standard_normal((B, D, H, W))).astype(np.float32)
     depth = synth.depth_per_pixel(D, H, W, 10.6, B) if per_pixel else synth.depth_planes(D, B)
     return dict(logits=logits, depth=depth)
+
+
+def geo_case(n_src=4, H=96, W=128, seed=7):
+    """Depth maps of a tilted world plane seen by a DTU-like rig (analytic per view), perturbed so that the
+    geometric-consistency masks are mixed: smooth ripples everywhere, gross outliers in blocks, a zero-depth hole.
+    float64 cameras [K 3x3, E 4x4] as read_camera_parameters returns them; float32 depth / confidence maps."""
+    rng = np.random.RandomState(seed)
+    n = n_src + 1
+    f = 2892.33 * W / 1600.0
+    K = np.array([[f, 0, W / 2 - 0.5 + 0.3], [0, f * 0.997, H / 2 - 0.5 - 0.2], [0, 0, 1]], np.float64)
+    Ks, Es, depths = [], [], []
+    normal = np.array([0.08, -0.05, 1.0]); normal /= np.linalg.norm(normal)
+    c = 680.0
+    for v in range(n):
+        ang = rng.uniform(-0.08, 0.08, 3) if v else np.zeros(3)
+        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+             np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+        t = rng.uniform(-60, 60, 3) * np.array([1, 1, 0.2]) if v else np.zeros(3)
+        E = np.eye(4); E[:3, :3] = R; E[:3, 3] = t
+        Kv = K.copy(); Kv[0, 2] += rng.uniform(-1, 1); Kv[1, 2] += rng.uniform(-1, 1)
+        ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+        k = np.linalg.inv(Kv) @ np.stack([xs.ravel(), ys.ravel(), np.ones(H * W)])
+        # plane normal . X_w = c with X_w = R^T (d k - t)  =>  d = (c + n.R^T t) / (n.R^T k)
+        nr = normal @ R.T
+        d = (c + nr @ t) / (nr @ k)
+        d = d.reshape(H, W)
+        d = d * (1 + 0.002 * np.sin(xs / 7.0 + v) * np.cos(ys / 5.0))           # ripples: borderline pixels
+        Ks.append(Kv); Es.append(E); depths.append(d.astype(np.float32))
+    # gross outliers / holes in the source maps, a hole in the reference map
+    for v in range(1, n):
+        y0, x0 = rng.randint(0, H - 24), rng.randint(0, W - 32)
+        depths[v][y0:y0 + 24, x0:x0 + 32] *= np.float32(1.05)
+        depths[v][rng.randint(0, H - 8):, :6] = 0
+    depths[0][5:9, 10:20] = 0
+    conf = rng.uniform(0.5, 1.0, (H, W)).astype(np.float32)
+    return dict(K=np.stack(Ks), E=np.stack(Es), depth=np.stack(depths), conf=conf)

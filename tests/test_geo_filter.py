@@ -1,0 +1,96 @@
+"""§8(f) f4 -- geometric-consistency filter: the oracle against the reference (+ real cv2) golden fixture on the CPU,
+the CUDA kernels against the oracle and the fixture on the GPU."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import geo_oracle as G
+
+
+def _views(g, v):
+    return g["depth"][0], g["K"][0], g["E"][0], g["depth"][v], g["K"][v], g["E"][v]
+
+
+def test_oracle_matches_reference_with_cv2():
+    """Bit-exact: the NumPy restatement (incl. the cv2.remap emulation) vs the reference's own functions run with cv2."""
+    g, gold = cases.geo_case(), cases.golden("geo_filter")
+    for v in range(1, g["depth"].shape[0]):
+        d_rep, x_rep, y_rep, x_src, y_src = G.reproject_with_depth(*_views(g, v))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mask, d_masked, _, _ = G.check_geometric_consistency(*_views(g, v))
+        for name, a in (("depth_reprojected", d_rep), ("x_reprojected", x_rep), ("y_reprojected", y_rep), ("x_src", x_src),
+                        ("y_src", y_src), ("mask", mask), ("depth_masked", d_masked)):
+            assert np.array_equal(a, gold[f"{name}_{v}"], equal_nan=True), (name, v)
+        assert 0.3 < mask.mean() < 0.95           # the case exercises both outcomes
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s, avg, _, gm, fm = G.fuse_ref_view(g["depth"][0], g["conf"], g["K"][0], g["E"][0], g["depth"][1:], g["K"][1:], g["E"][1:])
+    assert np.array_equal(s, gold["geo_mask_sum"]) and np.array_equal(avg, gold["depth_est_averaged"], equal_nan=True)
+    assert np.array_equal(gm, gold["geo_mask"]) and np.array_equal(fm, gold["final_mask"])
+
+
+def test_remap_emulation_known_answers():
+    src = np.arange(12, dtype=np.float32).reshape(3, 4)
+    x = np.array([[0.0, 1.5, 3.0, -1.0, 3.5, 1.0 + 1 / 64]], np.float32)
+    y = np.array([[0.0, 0.5, 2.0, 0.0, 2.5, 1.0]], np.float32)
+    out = G.remap_bilinear(src, x, y)
+    # integer position, centre of four pixels, last pixel, outside, half outside (border 0), 1/64 px rounds to even (=> 0)
+    assert out[0, 0] == 0 and out[0, 1] == (1 + 2 + 5 + 6) / 4 and out[0, 2] == 11 and out[0, 3] == 0
+    assert out[0, 4] == 11 / 4 and out[0, 5] == 5
+
+
+@pytest.mark.gpu
+def test_gpu_pair_matches_oracle_and_golden():
+    import torch
+    from mvs_b200 import fusion
+    g, gold = cases.geo_case(), cases.golden("geo_filter")
+    for v in range(1, g["depth"].shape[0]):
+        d_rep, x_rep, y_rep, x_src, y_src = fusion.reproject_with_depth(*_views(g, v))          # NumPy in -> NumPy out
+        assert isinstance(d_rep, np.ndarray) and d_rep.dtype == np.float32
+        # float64 chain on the GPU vs BLAS: identical after the float32 casts up to rare last-bit differences
+        for name, a in (("depth_reprojected", d_rep), ("x_reprojected", x_rep), ("y_reprojected", y_rep), ("x_src", x_src),
+                        ("y_src", y_src)):
+            ref = gold[f"{name}_{v}"]
+            np.testing.assert_allclose(a, ref, rtol=2e-7, atol=1e-6, equal_nan=True, err_msg=f"{name}_{v}")
+            assert (a != ref).mean() < 1e-3, (name, v, (a != ref).mean())
+        mask, d_masked, xs, ys = fusion.check_geometric_consistency(*_views(g, v))
+        assert mask.dtype == np.bool_
+        flips = mask != gold[f"mask_{v}"]
+        assert flips.mean() < 1e-4, flips.sum()
+        keep = ~flips
+        np.testing.assert_allclose(d_masked[keep], gold[f"depth_masked_{v}"][keep], rtol=2e-7, atol=1e-6)
+        # CUDA tensors in -> CUDA tensors out
+        t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() if a.ndim == 2 and a.dtype == np.float32 else a for a in _views(g, v)]
+        m2 = fusion.check_geometric_consistency(*t)[0]
+        assert m2.is_cuda and np.array_equal(m2.cpu().numpy(), mask)
+
+
+@pytest.mark.gpu
+def test_gpu_fused_view_matches_golden():
+    from mvs_b200 import fusion
+    g, gold = cases.geo_case(), cases.golden("geo_filter")
+    out = fusion.fuse_ref_view(g["depth"][0], g["conf"], g["K"][0], g["E"][0], list(g["depth"][1:]), list(g["K"][1:]),
+                               list(g["E"][1:]), per_source=True)
+    same = out["geo_mask_sum"] == gold["geo_mask_sum"]
+    assert same.mean() > 1 - 1e-4
+    assert out["depth_est_averaged"].dtype == np.float64
+    np.testing.assert_allclose(out["depth_est_averaged"][same], gold["depth_est_averaged"][same], rtol=3e-7, equal_nan=True)
+    assert (out["final_mask"] != gold["final_mask"]).mean() < 1e-4
+    assert np.array_equal(out["geo_mask"], out["geo_mask_sum"] >= 3)
+    for v in range(4):
+        assert (out["all_srcview_geomask"][v] != gold[f"mask_{v + 1}"]).mean() < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_properties():
+    """BASELINE cfg3 image size (1184x1600), 10 source views: identical cameras + identical depth maps => every pixel with
+    positive depth is consistent with every view and the fused depth equals the input (a size-independent property)."""
+    import torch
+    from mvs_b200 import fusion
+    g = cases.geo_case(n_src=1, H=1184, W=1600)
+    d = torch.from_numpy(g["depth"][0]).cuda()
+    conf = torch.ones_like(d)
+    out = fusion.fuse_ref_view(d, conf, g["K"][0], g["E"][0], [d] * 10, [g["K"][0]] * 10, [g["E"][0]] * 10)
+    ok = d > 0
+    assert bool((out["geo_mask_sum"][ok] == 10).all())
+    assert torch.allclose(out["depth_est_averaged"][ok], d[ok].double(), rtol=1e-6)
+    assert bool((out["final_mask"] == ok).all())
