@@ -101,6 +101,7 @@ struct ConvPlan {
     // the epilogue adds the three step-tap partials of an output step (slabs s, s+1, s+2).
     long long *trace;                               // profiling hook (mvs_conv3d_c8_set_trace): per-CTA role timers, or null
     int trace_ctas;
+    uint32_t ring_magic;                            // (1 << 18) / ring + 1: x / ring == (x * ring_magic) >> 18 for x < 32768
     int tmerged, buf_cols, prefetch;                // prefetch: slabs in flight per producer thread (<= ring - 1)
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
@@ -177,6 +178,10 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 // Role timers of the profiling hook: slot k of CTA c accumulates clock64 deltas at trace[c * 16 + k].
 //   0 CTA total | 1 producer wait empty | 2 producer stage+publish | 3 issuer wait full | 4 issuer wait tempty
 //   5 issuer issue | 6 epilogue wait tfull | 7 epilogue work | 9 prologue (until roles start) | 10 steps
+// x / ring and x % ring without a hardware-less integer division (~25 dependent instructions each): exact for x < 32768
+__device__ __forceinline__ int div_ring(int x, uint32_t magic) { return (int)(((uint32_t)x * magic) >> 18); }
+__device__ __forceinline__ int mod_ring(int x, int ring, uint32_t magic) { return x - div_ring(x, magic) * ring; }
+
 struct RoleTimer {          // accumulates in registers (a global read-modify-write per lap would cost ~700 clk each)
     long long *p; long long t, a0, a1, a2;
     int k0;
@@ -343,7 +348,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int m = ew * 32 + lane;                                 // row of the M tile owned by this thread
         const uint32_t lane_base = taddr + ((uint32_t)(ew * 32) << 16);
         const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
-        const int n3 = 3 * P.n, nb = P.n >> 3;
+        const int n3 = 3 * P.n, nb = P.n >> 3, nb_shift = nb == 4 ? 2 : (nb == 2 ? 1 : 0);
         const int my_rows = (P.ht - eg + 1) >> 1, n_items = my_rows * nb;
         const int ow = m0 + m;
         // output index of (row a, step): pos0 + a * row_stride + step * step_stride  (hoisted 64-bit arithmetic)
@@ -362,7 +367,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         for (int step = 0; step < nsteps; ++step) {
             // earlier slabs were waited for in earlier steps
             for (int sl = step == 0 ? 0 : step + 2; sl <= step + 2; ++sl)
-                mbar_wait(tfull + (sl & (UM_TBUFS - 1)), (uint32_t)(sl / UM_TBUFS) & 1u);
+                mbar_wait(tfull + (sl & (UM_TBUFS - 1)), (uint32_t)(sl >> 2) & 1u);
             rt.lap(6);
             tc_fence_after();
             uint32_t tcol[3];
@@ -429,9 +434,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     reinterpret_cast<uint4 *>(y)[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 };
                 for (int it = 0; it < n_items; it += 2) {
-                    const int a0 = eg + 2 * (it / nb), n00 = (it % nb) * 8;
+                    // nb = n / 8 is 1, 2 or 4: shifts instead of runtime divisions (a division is ~25 dependent
+                    // instructions = ~125 clk of this warp)
+                    const int a0 = eg + 2 * (it >> nb_shift), n00 = (it & (nb - 1)) * 8;
                     const bool two = it + 1 < n_items;
-                    const int a1 = eg + 2 * ((it + 1) / nb), n01 = ((it + 1) % nb) * 8;
+                    const int a1 = eg + 2 * ((it + 1) >> nb_shift), n01 = ((it + 1) & (nb - 1)) * 8;
                     uint32_t p0[8], p1[8], p2[8], q0[8], q1[8], q2[8];
                     const uint32_t c0 = (uint32_t)(a0 * n3 + n00), c1 = (uint32_t)(a1 * n3 + n01);
                     tmem_ld8_nowait(tcol[0] + c0, p0);
@@ -495,8 +502,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             // does any line of this warp need zero columns / zero rows in an in-range slab?
             const bool edge_cols = c_lo > 0 || c_hi < UM_COLS;
             const bool edge_rows = __any_sync(0xffffffffu, ln < lines && !(my_h >= 0 && my_h < P.H));
-            for (int i = 0; i < n_slabs; ++i) {
-                const int slot = i % P.ring, q = i / P.ring;
+            int slot = 0, q = 0;                       // i = q * ring + slot, kept incrementally (no divisions per slab)
+            for (int i = 0; i < n_slabs; ++i, slot = slot + 1 == P.ring ? 0 : slot + 1, q += slot == 0 ? 1 : 0) {
                 if (q >= 1) mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
                 rt.lap(1);
                 const int d_in = P.d_base + step_begin + i;
@@ -526,14 +533,14 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             rt.flush();
         } else
         for (int i = 0; i < n_slabs; ++i) {
-            const int slot = i % P.ring, q = i / P.ring;
+            const int q = div_ring(i, P.ring_magic), slot = i - q * P.ring;
             if (q >= 1) {
                 // never block on `empty` while holding an unpublished slab: the issuer may need it to
                 // retire the very slab we are waiting for (ring == rd leaves no slack)
                 if (pending >= 0) {
                     cp_async_wait<0>();
                     fence_async_smem();
-                    mbar_arrive(full + pending % P.ring);
+                    mbar_arrive(full + mod_ring(pending, P.ring, P.ring_magic));
                     pending = -1;
                 }
                 mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
@@ -562,14 +569,14 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             if (pending >= 0) {        // the previous slab has landed for this thread: publish it
                 cp_async_wait<1>();
                 fence_async_smem();
-                mbar_arrive(full + pending % P.ring);
+                mbar_arrive(full + mod_ring(pending, P.ring, P.ring_magic));
             }
             pending = i;
         }
         if (pending >= 0) {
             cp_async_wait<0>();
             fence_async_smem();
-            mbar_arrive(full + pending % P.ring);
+            mbar_arrive(full + mod_ring(pending, P.ring, P.ring_magic));
         }
     } else if (warp >= 8 && warp < 12) {
         // =========================== MMA issuers ======================================================
@@ -592,9 +599,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 const uint32_t idesc0 = umma_idesc_bf16(128, 0);
                 constexpr uint32_t kDescHi = 8u | (1u << 14);
                 RoleTimer rt; rt.start(trace && lane == 0 && iss == 0, trace, 3);
+                int slot = iss, q = 0;                     // sl = q * ring + slot (ring is even and >= 2, so slot = iss < ring)
                 for (int sl = iss; sl < n_slabs; sl += 2) {
-                    const int slot = sl % P.ring, buf = sl & (UM_TBUFS - 1), use = sl / UM_TBUFS;
-                    mbar_wait(full + slot, (uint32_t)(sl / P.ring) & 1u);
+                    const int buf = sl & (UM_TBUFS - 1), use = sl >> 2;
+                    static_assert(UM_TBUFS == 4, "use = sl >> 2");
+                    mbar_wait(full + slot, (uint32_t)q & 1u);
                     rt.lap(3);
                     if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
                     rt.lap(4);
@@ -631,6 +640,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     }
                     __syncwarp();
                     rt.lap(5);
+                    slot += 2;
+                    if (slot >= P.ring) { slot -= P.ring; ++q; }
                 }
                 rt.flush();
             }
@@ -651,7 +662,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 // barrier whose slot may already have been released and refilled (the phase would alias)
                 if (waited < first) waited = first;
                 while (waited < first + P.rd) {
-                    mbar_wait(full + waited % P.ring, (uint32_t)(waited / P.ring) & 1u);
+                    const int wq = div_ring(waited, P.ring_magic);
+                    mbar_wait(full + (waited - wq * P.ring), (uint32_t)wq & 1u);
                     ++waited;
                 }
                 const int buf = step & 1, use = step >> 1;
@@ -661,7 +673,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 // ops are grouped by the depth slab they read, so the slab base is loop-invariant and an op
                 // costs one 16 B constant load + three adds + the predicate in the uniform datapath
                 for (int r = 0; r < P.rd; ++r) {
-                    const uint32_t base = sa_units + (uint32_t)(((first + r) % P.ring) * P.slab_units);
+                    const uint32_t base = sa_units + (uint32_t)(mod_ring(first + r, P.ring, P.ring_magic) * P.slab_units);
                     const int op0 = P.op_begin[tbl][r], op1 = P.op_begin[tbl][r + 1];
                     int i = op0;
                     for (; i + 4 <= op1; i += 4) {
@@ -692,7 +704,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     // slabs the next step no longer reads go back to the producers once these MMAs retire
                     // (merged mode: another issuer's step may still read them -> the epilogue frees them)
                     if (!P.merged)
-                        for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + (first + k) % P.ring);
+                        for (int k = 0; k < P.d_mul; ++k) umma_commit(empty + mod_ring(first + k, P.ring, P.ring_magic));
                     umma_commit(tfull + buf);
                 }
                 __syncwarp();
@@ -709,7 +721,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             if (P.merged && tid == 0) {
                 // steps complete in order as seen from here (we waited on every earlier tfull), so no MMA of
                 // any step <= `step` still reads the slabs this step retires
-                for (int k = 0; k < P.d_mul; ++k) mbar_arrive(empty + (P.d_mul * step + k) % P.ring);
+                for (int k = 0; k < P.d_mul; ++k) mbar_arrive(empty + mod_ring(P.d_mul * step + k, P.ring, P.ring_magic));
             }
             const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
             const uint32_t tcol0 = lane_base + (uint32_t)(buf * P.acc_cols);
@@ -1290,6 +1302,8 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
         return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_fwd: no tile configuration fits shared memory / TMEM for this layer");
     MVS_REQUIRE(!(out_f32 && skip_c8), "skip is not supported on the fp32 (Cout == 1) output");
     P.trace = g_trace; P.trace_ctas = g_trace_ctas;
+    P.ring_magic = (1u << 18) / (uint32_t)P.ring + 1u;
+    MVS_REQUIRE(2 * P.steps + 4 < 32768, "step axis too long for the slab-ring arithmetic");
     P.swap = kStepAlongH ? 1 : 0;
     P.Dr = D; P.Hr = H;
     P.Dor = kStepAlongH ? P.Ho : P.Do;
