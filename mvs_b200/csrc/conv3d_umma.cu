@@ -287,6 +287,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     float *s_shift = s_scale + 32;                                   // [n] shift
     // [lines] per staged line: vector offset of (line, step 0, w 0) in x, or ~0 for a line outside the volume
     unsigned long long *s_line = reinterpret_cast<unsigned long long *>(s_shift + 32);
+    // [n_acc] per accumulator: x = voxel offset of (its row, step 0, w 0), y = dd | wadd << 8 | row-in-range << 16
+    ulonglong2 *s_acc = reinterpret_cast<ulonglong2 *>(s_line + UM_MAX_LINES);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch, issuer id)
@@ -316,6 +318,16 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int c = ct * P.n + tid;
         s_scale[tid] = c < P.cout ? (scale ? __ldg(scale + c) : 1.f) : 0.f;
         s_shift[tid] = c < P.cout ? (shift ? __ldg(shift + c) : 0.f) : 0.f;
+    }
+    if (!TM && tid < P.n_acc) {
+        // epilogue accumulator table: the step-invariant part of out_pos (the per-step 64-bit index arithmetic and the
+        // dynamically indexed reads of P.acc were ~25 dependent instructions per accumulator and step)
+        const AccOut ao = P.acc[tid];
+        const int oh = P.oh_mul * (h0 + ao.th) + ao.dh, od0 = P.od_mul * step_begin + ao.dd;
+        const size_t plane_o = (size_t)P.Hor * P.Wo;
+        const size_t off = P.swap ? (size_t)oh * plane_o + (size_t)od0 * P.Wo : (size_t)od0 * plane_o + (size_t)oh * P.Wo;
+        s_acc[tid] = make_ulonglong2((unsigned long long)(off + (size_t)ao.wadd),
+                                     (unsigned long long)((uint32_t)ao.dd | ((uint32_t)ao.wadd << 8) | ((oh < P.Ho ? 1u : 0u) << 16)));
     }
     if (!TM) {
         // producer line table: everything about a staged line that does not depend on the slab
@@ -356,6 +368,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const size_t row_stride = P.swap ? plane_o : (size_t)P.Wo, step_stride = P.swap ? (size_t)P.Wo : plane_o;
         const size_t pos0 = (size_t)h0 * row_stride + (size_t)step_begin * step_stride + (size_t)ow;
         const bool w_ok = ow < P.Wo;
+        const size_t chunk_base = ((size_t)b * P.cout_chunks + (size_t)ct * nb) * vol_o;
         // folded-BN affine of the first 8-channel block in registers (the only block when Cout <= 8)
         float2 sc2[4], sh2[4];
 #pragma unroll
@@ -401,9 +414,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 }
             } else {
                 auto finish = [&](const uint32_t (&r0)[8], const uint32_t (&r1)[8], const uint32_t (&r2)[8], int a, int n0) {
-                    const int cc = ct * P.n + n0;
-                    if (!w_ok || h0 + a >= P.Ho || cc >= P.cout_chunks * 8) return;
-                    const size_t oidx = ((size_t)b * P.cout_chunks + (cc >> 3)) * vol_o + pos_step + (size_t)a * row_stride;
+                    const int cb = ct * nb + (n0 >> 3);                       // output channel block
+                    if (!w_ok || h0 + a >= P.Ho || cb >= P.cout_chunks) return;
+                    const size_t oidx = chunk_base + (size_t)(n0 >> 3) * vol_o + pos_step + (size_t)a * row_stride;
                     uint4 sk = make_uint4(0, 0, 0, 0);
                     if (P.has_skip) sk = __ldg(skip + oidx);
                     float2 scl[4], shl[4];
@@ -714,6 +727,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         // =========================== epilogue: TMEM -> registers -> global ============================
         const int m = warp * 32 + lane;                               // row of the M tile owned by this thread
         const uint32_t lane_base = taddr + ((uint32_t)(warp * 32) << 16);
+        const int ow_thread = P.w_mul * (m0 + m);                     // + wadd = output w
+        const size_t epi_step_stride = P.swap ? (size_t)P.Wo : (size_t)P.Hor * P.Wo;
         for (int step = 0; step < nsteps; ++step) {
             const int buf = step & 1, use = step >> 1;
             mbar_wait(tfull + buf, (uint32_t)use & 1u);
@@ -754,14 +769,13 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
                 reinterpret_cast<uint4 *>(y)[oidx] = pk;
             };
+            const int od_step = P.od_mul * (step_begin + step);                   // + dd = output position on the step axis
+            const size_t step_off = (size_t)(P.od_mul * step) * epi_step_stride + (size_t)ow_thread;
             auto out_pos = [&](int a, bool &ok) -> size_t {      // voxel index of accumulator a's row for this thread
-                const AccOut ao = P.acc[a];
-                const int od = P.od_mul * (step_begin + step) + ao.dd;
-                const int oh = P.oh_mul * (h0 + ao.th) + ao.dh;
-                const int ow = P.w_mul * (m0 + m) + ao.wadd;
-                ok = od < P.Do && oh < P.Ho && ow < P.Wo;
-                const int odr = P.swap ? oh : od, ohr = P.swap ? od : oh;                 // real (d, h)
-                return ((size_t)odr * P.Hor + ohr) * P.Wo + ow;
+                const ulonglong2 e = s_acc[a];
+                const uint32_t f = (uint32_t)e.y;
+                ok = (f >> 16) != 0 && od_step + (int)(f & 0xffu) < P.Do && ow_thread + (int)((f >> 8) & 0xffu) < P.Wo;
+                return (size_t)e.x + step_off;
             };
             if (P.out_f32) {
                 // `prob` layer: one real channel -> fp32 logits; four rows' single-column loads per wait
@@ -1016,7 +1030,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
 
 static size_t plan_smem_bytes(int weight_units, int ring, int slab_units)
 {
-    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 2 * UM_TBUFS) * 8 + 16 + 64 * 4 + UM_MAX_LINES * 8;
+    return ((size_t)weight_units + (size_t)ring * slab_units) * 16 + (2 * UM_MAX_RING + 2 * UM_TBUFS) * 8 + 16 + 64 * 4 + UM_MAX_LINES * 8 + UM_MAX_ACC * 16;
 }
 
 static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout, int D, int H, int W, int stride,
