@@ -369,6 +369,12 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const size_t pos0 = (size_t)h0 * row_stride + (size_t)step_begin * step_stride + (size_t)ow;
         const bool w_ok = ow < P.Wo;
         const size_t chunk_base = ((size_t)b * P.cout_chunks + (size_t)ct * nb) * vol_o;
+        // 64-bit bases once per thread, 32-bit offsets in the loops (ptxas re-materialised the 64-bit index arithmetic per
+        // row otherwise: ~50 of the ~140 instructions a row cost).  The launcher checks that the offsets fit 32 bits.
+        uint4 *const ybase = reinterpret_cast<uint4 *>(y) + chunk_base + pos0;
+        const uint4 *const sbase = skip + chunk_base + pos0;
+        float *const fbase = reinterpret_cast<float *>(y) + (size_t)b * vol_o + pos0;
+        const uint32_t rs32 = (uint32_t)row_stride, ss32 = (uint32_t)step_stride, vo32 = (uint32_t)vol_o;
         // folded-BN affine of the first 8-channel block in registers (the only block when Cout <= 8)
         float2 sc2[4], sh2[4];
 #pragma unroll
@@ -387,10 +393,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 #pragma unroll
             for (int t = 0; t < 3; ++t)
                 tcol[t] = lane_base + (uint32_t)(((step + t) & (UM_TBUFS - 1)) * P.buf_cols + t * P.n);
-            const size_t pos_step = pos0 + (size_t)step * step_stride;
+            const uint32_t so = (uint32_t)step * ss32;
             if (P.out_f32) {
                 // `prob`: one real channel -> fp32 logits; up to four rows (12 single-column loads) per wait
-                float *yo = reinterpret_cast<float *>(y) + (size_t)b * vol_o + pos_step;
+                float *yo = fbase + so;
                 for (int j0 = 0; j0 < my_rows; j0 += 4) {
                     uint32_t r[4][3];
 #pragma unroll
@@ -409,26 +415,17 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         const float acc = (__uint_as_float(r[j][0]) + __uint_as_float(r[j][1])) + __uint_as_float(r[j][2]);
                         float o = fmaf(acc, sc2[0].x, sh2[0].x);
                         if (P.relu) o = fmaxf(o, 0.f);
-                        yo[(size_t)a * row_stride] = o;
+                        yo[(uint32_t)a * rs32] = o;
                     }
                 }
             } else {
-                auto finish = [&](const uint32_t (&r0)[8], const uint32_t (&r1)[8], const uint32_t (&r2)[8], int a, int n0) {
+                auto finish_with = [&](const uint32_t (&r0)[8], const uint32_t (&r1)[8], const uint32_t (&r2)[8], int a, int n0,
+                                       const float2 (&scl)[4], const float2 (&shl)[4]) {
                     const int cb = ct * nb + (n0 >> 3);                       // output channel block
                     if (!w_ok || h0 + a >= P.Ho || cb >= P.cout_chunks) return;
-                    const size_t oidx = chunk_base + (size_t)(n0 >> 3) * vol_o + pos_step + (size_t)a * row_stride;
+                    const uint32_t oidx = so + (uint32_t)a * rs32 + (uint32_t)(n0 >> 3) * vo32;
                     uint4 sk = make_uint4(0, 0, 0, 0);
-                    if (P.has_skip) sk = __ldg(skip + oidx);
-                    float2 scl[4], shl[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { scl[e] = sc2[e]; shl[e] = sh2[e]; }
-                    if (n0 != 0) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            scl[e] = make_float2(s_scale[n0 + 2 * e], s_scale[n0 + 2 * e + 1]);
-                            shl[e] = make_float2(s_shift[n0 + 2 * e], s_shift[n0 + 2 * e + 1]);
-                        }
-                    }
+                    if (P.has_skip) sk = __ldg(sbase + oidx);
                     const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
                     uint32_t pk[4];
 #pragma unroll
@@ -444,7 +441,18 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         }
                         pk[e] = pack_bf16x2(v.x, v.y);
                     }
-                    reinterpret_cast<uint4 *>(y)[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    ybase[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                };
+                // one channel block (Cout <= 8): the affine lives in registers; otherwise it is read per block
+                auto finish = [&](const uint32_t (&r0)[8], const uint32_t (&r1)[8], const uint32_t (&r2)[8], int a, int n0) {
+                    if (nb == 1) { finish_with(r0, r1, r2, a, n0, sc2, sh2); return; }
+                    float2 scl[4], shl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        scl[e] = make_float2(s_scale[n0 + 2 * e], s_scale[n0 + 2 * e + 1]);
+                        shl[e] = make_float2(s_shift[n0 + 2 * e], s_shift[n0 + 2 * e + 1]);
+                    }
+                    finish_with(r0, r1, r2, a, n0, scl, shl);
                 };
                 for (int it = 0; it < n_items; it += 2) {
                     // nb = n / 8 is 1, 2 or 4: shifts instead of runtime divisions (a division is ~25 dependent
@@ -1317,6 +1325,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     MVS_REQUIRE(!(out_f32 && skip_c8), "skip is not supported on the fp32 (Cout == 1) output");
     P.trace = g_trace; P.trace_ctas = g_trace_ctas;
     P.ring_magic = (1u << 18) / (uint32_t)P.ring + 1u;
+    MVS_REQUIRE((long long)P.Do * P.Ho * P.Wo * (P.n >> 3 > 0 ? P.n >> 3 : 1) < (1ll << 31), "output volume too large for 32-bit tile offsets");
     MVS_REQUIRE(2 * P.steps + 4 < 32768, "step axis too long for the slab-ring arithmetic");
     P.swap = kStepAlongH ? 1 : 0;
     P.Dr = D; P.Hr = H;
