@@ -326,7 +326,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int oh = P.oh_mul * (h0 + ao.th) + ao.dh, od0 = P.od_mul * step_begin + ao.dd;
         const size_t plane_o = (size_t)P.Hor * P.Wo;
         const size_t off = P.swap ? (size_t)oh * plane_o + (size_t)od0 * P.Wo : (size_t)od0 * plane_o + (size_t)oh * P.Wo;
-        s_acc[tid] = make_ulonglong2((unsigned long long)(off + (size_t)ao.wadd),
+        s_acc[tid] = make_ulonglong2((unsigned long long)(uint32_t)(off + (size_t)ao.wadd),
                                      (unsigned long long)((uint32_t)ao.dd | ((uint32_t)ao.wadd << 8) | ((oh < P.Ho ? 1u : 0u) << 16)));
     }
     if (!TM) {
@@ -736,7 +736,21 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int m = warp * 32 + lane;                               // row of the M tile owned by this thread
         const uint32_t lane_base = taddr + ((uint32_t)(warp * 32) << 16);
         const int ow_thread = P.w_mul * (m0 + m);                     // + wadd = output w
-        const size_t epi_step_stride = P.swap ? (size_t)P.Wo : (size_t)P.Hor * P.Wo;
+        const uint32_t epi_step_stride = (uint32_t)(P.swap ? (size_t)P.Wo : (size_t)P.Hor * P.Wo) * (uint32_t)P.od_mul;
+        // 64-bit bases once per thread, 32-bit voxel offsets in the loops (the launcher checks the volume fits 31 bits)
+        const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
+        const uint32_t vo32 = (uint32_t)vol_o;
+        const size_t tile_base = ((size_t)b * P.cout_chunks + (size_t)((ct * P.n) >> 3)) * vol_o;
+        uint4 *const ybase = reinterpret_cast<uint4 *>(y) + tile_base;
+        const uint4 *const sbase = skip + tile_base;
+        float *const fbase = reinterpret_cast<float *>(y) + (size_t)b * vol_o;
+        // folded-BN affine of the first 8-channel block in registers (the only block when Cout <= 8)
+        float2 sc2[4], sh2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sc2[e] = make_float2(s_scale[2 * e], s_scale[2 * e + 1]);
+            sh2[e] = make_float2(s_shift[2 * e], s_shift[2 * e + 1]);
+        }
         for (int step = 0; step < nsteps; ++step) {
             const int buf = step & 1, use = step >> 1;
             mbar_wait(tfull + buf, (uint32_t)use & 1u);
@@ -746,44 +760,42 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 // any step <= `step` still reads the slabs this step retires
                 for (int k = 0; k < P.d_mul; ++k) mbar_arrive(empty + mod_ring(P.d_mul * step + k, P.ring, P.ring_magic));
             }
-            const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
             const uint32_t tcol0 = lane_base + (uint32_t)(buf * P.acc_cols);
             // affine + ReLU + skip + store of one 8-channel block held in v[0..7]
             // (the skip operand is fetched by the caller BEFORE the TMEM wait: issued one at a time next to its use,
             // every skip load costs a full DRAM round trip of this warp)
-            auto store_chunk = [&](const uint32_t (&v)[8], int nloc, size_t oidx, const uint4 &sk) {
-                const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + nloc);
-                const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + nloc);
-                const float4 sa = sc4[0], sb = sc4[1], ha = sh4[0], hb = sh4[1];
-                const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-                const float shv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-                float o[8];
+            auto store_with = [&](const uint32_t (&v)[8], uint32_t oidx, const uint4 &sk, const float2 (&scl)[4],
+                                  const float2 (&shl)[4]) {
+                const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
+                uint32_t pk[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float t = fmaf(__uint_as_float(v[e]), scv[e], shv[e]);
-                    if (P.relu) t = fmaxf(t, 0.f);
-                    o[e] = t;
-                }
-                if (P.has_skip) {
-                    const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        o[2 * e] += __uint_as_float(sv[e] << 16);
-                        o[2 * e + 1] += __uint_as_float(sv[e] & 0xffff0000u);
+                for (int e = 0; e < 4; ++e) {
+                    float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), scl[e], shl[e]);
+                    if (P.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); }
+                    if (P.has_skip) {
+                        t.x += __uint_as_float(sv[e] << 16);
+                        t.y += __uint_as_float(sv[e] & 0xffff0000u);
                     }
+                    pk[e] = pack_bf16x2(t.x, t.y);
                 }
-                uint4 pk;
-                pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-                pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-                reinterpret_cast<uint4 *>(y)[oidx] = pk;
+                ybase[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            };
+            auto store_chunk = [&](const uint32_t (&v)[8], int nloc, uint32_t oidx, const uint4 &sk) {
+                float2 scl[4], shl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    scl[e] = make_float2(s_scale[nloc + 2 * e], s_scale[nloc + 2 * e + 1]);
+                    shl[e] = make_float2(s_shift[nloc + 2 * e], s_shift[nloc + 2 * e + 1]);
+                }
+                store_with(v, oidx, sk, scl, shl);
             };
             const int od_step = P.od_mul * (step_begin + step);                   // + dd = output position on the step axis
-            const size_t step_off = (size_t)(P.od_mul * step) * epi_step_stride + (size_t)ow_thread;
-            auto out_pos = [&](int a, bool &ok) -> size_t {      // voxel index of accumulator a's row for this thread
+            const uint32_t step_off = (uint32_t)step * epi_step_stride + (uint32_t)ow_thread;
+            auto out_pos = [&](int a, bool &ok) -> uint32_t {    // voxel offset of accumulator a's row for this thread
                 const ulonglong2 e = s_acc[a];
                 const uint32_t f = (uint32_t)e.y;
                 ok = (f >> 16) != 0 && od_step + (int)(f & 0xffu) < P.Do && ow_thread + (int)((f >> 8) & 0xffu) < P.Wo;
-                return (size_t)e.x + step_off;
+                return (uint32_t)e.x + step_off;
             };
             if (P.out_f32) {
                 // `prob` layer: one real channel -> fp32 logits; four rows' single-column loads per wait
@@ -797,11 +809,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     for (int j = 0; j < 4; ++j) {
                         if (a0 + j >= P.n_acc) break;
                         bool ok;
-                        const size_t pos = out_pos(a0 + j, ok);
+                        const uint32_t pos = out_pos(a0 + j, ok);
                         if (!ok) continue;
-                        float o = fmaf(__uint_as_float(r[j]), s_scale[0], s_shift[0]);
+                        float o = fmaf(__uint_as_float(r[j]), sc2[0].x, sh2[0].x);
                         if (P.relu) o = fmaxf(o, 0.f);
-                        reinterpret_cast<float *>(y)[(size_t)b * vol_o + pos] = o;
+                        fbase[pos] = o;
                     }
                 }
             } else if (P.cout <= 8) {
@@ -810,7 +822,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 constexpr int EB = MC >= 3 ? 2 : 4;
                 for (int a0 = 0; a0 < P.n_acc; a0 += EB) {
                     uint32_t r[EB][8];
-                    size_t pos[EB];
+                    uint32_t pos[EB];
                     bool ok[EB];
                     uint4 sk[EB];
 #pragma unroll
@@ -818,29 +830,29 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         ok[j] = false;
                         sk[j] = make_uint4(0, 0, 0, 0);
                         if (a0 + j < P.n_acc) {
-                            pos[j] = (size_t)b * P.cout_chunks * vol_o + out_pos(a0 + j, ok[j]);
-                            if (P.has_skip && ok[j]) sk[j] = __ldg(skip + pos[j]);
+                            pos[j] = out_pos(a0 + j, ok[j]);
+                            if (P.has_skip && ok[j]) sk[j] = __ldg(sbase + pos[j]);
                             tmem_ld8_nowait(tcol0 + (uint32_t)((a0 + j) * P.n), r[j]);
                         }
                     }
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < EB; ++j)
-                        if (ok[j]) store_chunk(r[j], 0, pos[j], sk[j]);
+                        if (ok[j]) store_with(r[j], pos[j], sk[j], sc2, sh2);
                 }
             } else {
                 for (int a = 0; a < P.n_acc; ++a) {
                     bool ok;
-                    const size_t pos = out_pos(a, ok);
+                    const uint32_t pos = out_pos(a, ok);
                     for (int n0 = 0; n0 < P.n; n0 += 16) {
                         uint32_t r[16];
                         const int c0 = ct * P.n + n0;
                         const bool live = ok && c0 < P.cout, has_hi = c0 + 8 < P.cout_chunks * 8;
-                        const size_t base = ((size_t)b * P.cout_chunks + (c0 >> 3)) * vol_o + pos;
+                        const uint32_t base = (uint32_t)(n0 >> 3) * vo32 + pos;
                         uint4 sk_lo = make_uint4(0, 0, 0, 0), sk_hi = make_uint4(0, 0, 0, 0);
                         if (P.has_skip && live) {
-                            sk_lo = __ldg(skip + base);
-                            if (has_hi) sk_hi = __ldg(skip + base + vol_o);
+                            sk_lo = __ldg(sbase + base);
+                            if (has_hi) sk_hi = __ldg(sbase + base + vo32);
                         }
                         tmem_ld16_nowait(tcol0 + (uint32_t)(a * P.n + n0), r);
                         tmem_wait_ld();
@@ -849,7 +861,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 #pragma unroll
                         for (int e = 0; e < 8; ++e) { lo[e] = r[e]; hi[e] = r[8 + e]; }
                         store_chunk(lo, n0, base, sk_lo);
-                        if (has_hi) store_chunk(hi, n0 + 8, base + vol_o, sk_hi);
+                        if (has_hi) store_chunk(hi, n0 + 8, base + vo32, sk_hi);
                     }
                 }
             }
