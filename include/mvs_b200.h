@@ -188,6 +188,10 @@ int mvs_cas_hypotheses(const float *prev_depth, int hp, int wp, int H, int W, in
 int mvs_geo_consistency(const float *depth_ref, const float *depth_src, const double *cam, uint8_t *mask,
                         float *depth_reproj, float *x_src, float *y_src, float *x_rep, float *y_rep, int H, int W,
                         double dist_thresh, float rel_thresh, int apply_mask, void *stream);
+/* Back-projection of a fused depth map (float64 [H,W], as mvs_geo_fuse writes it) to world points, MVSNet/eval.py:297-300:
+ * cam = inv(K_ref)[9] | inv(E_ref)[:3][12] (device, float64).  xyz float32 [H,W,3]; NaN where mask (u8, optional) is 0. */
+int mvs_geo_backproject(const double *depth, const uint8_t *mask, const double *cam, float *xyz, int H, int W,
+                        void *stream);
 int mvs_geo_fuse(const float *depth_ref, const float *conf, const void *const *depth_srcs_host, int nsrc,
                  const double *cams, int32_t *geo_sum, double *depth_avg, uint8_t *final_mask, uint8_t *geo_masks,
                  float *depth_reproj, int H, int W, double dist_thresh, float rel_thresh, float conf_thresh,

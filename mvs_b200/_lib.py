@@ -51,6 +51,7 @@ SIGNATURES = {
     "mvs_softargmin_conf_fwd": (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i] * 5 + [_vp]),
     "mvs_depth_range_samples": (_i, [_vp, _d, _i, _vp, _i, _i, _i, _vp]),
     "mvs_geo_consistency": (_i, [_vp] * 9 + [_i, _i, _d, C.c_float, _i, _vp]),
+    "mvs_geo_backproject": (_i, [_vp] * 4 + [_i, _i, _vp]),
     "mvs_geo_fuse": (_i, [_vp, _vp, _vp, _i] + [_vp] * 6 + [_i, _i, _d, C.c_float, C.c_float, _i, _vp]),
     "mvs_cas_hypotheses": (_i, [_vp] + [_i] * 7 + [_d, _vp, _i, _vp]),
 }

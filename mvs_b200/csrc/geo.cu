@@ -140,9 +140,46 @@ geo_fuse_kernel(const float *__restrict__ depth_ref, const float *__restrict__ c
     if (final_mask) final_mask[i] = (cnt >= min_views && __ldg(conf + i) > conf_thresh) ? 1 : 0;
 }
 
+// Back-projection of the fused depth map to world points: filter_depth, MVSNet/eval.py:297-300
+//   xyz_ref = inv(K_ref) @ (x*d, y*d, d);  xyz_world = (inv(E_ref) @ (xyz_ref, 1))[:3]      (float64, stored as float32)
+// cam: inv(K_ref)[9] | inv(E_ref)[:3][12].  Dense output [H,W,3]; pixels outside `mask` get NaN (callers compact with it).
+__global__ void __launch_bounds__(256)
+geo_backproject_kernel(const double *__restrict__ depth, const uint8_t *__restrict__ mask, const double *__restrict__ cam,
+                       float *__restrict__ xyz, int H, int W)
+{
+    __shared__ double s_cam[21];
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    if (t < 21) s_cam[t] = cam[t];
+    __syncthreads();
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t i = (size_t)y * W + x;
+    float ox = __int_as_float(0x7fc00000), oy = ox, oz = ox;
+    if (!mask || mask[i]) {
+        const double d = depth[i];
+        const double px = (double)x * d, py = (double)y * d, pz = 1.0 * d;
+        const double rx = dot3(s_cam, px, py, pz), ry = dot3(s_cam + 3, px, py, pz), rz = dot3(s_cam + 6, px, py, pz);
+        ox = (float)dot4h(s_cam + 9, rx, ry, rz);
+        oy = (float)dot4h(s_cam + 13, rx, ry, rz);
+        oz = (float)dot4h(s_cam + 17, rx, ry, rz);
+    }
+    xyz[3 * i] = ox; xyz[3 * i + 1] = oy; xyz[3 * i + 2] = oz;
+}
+
 }  // namespace mvs
 
 using namespace mvs;
+
+extern "C" int mvs_geo_backproject(const double *depth, const uint8_t *mask, const double *cam, float *xyz, int H, int W,
+                                   void *stream)
+{
+    if (H == 0 || W == 0) return MVS_OK;
+    MVS_REQUIRE(H > 0 && W > 0, "extents must be positive");
+    MVS_REQUIRE(depth && cam && xyz, "null pointer");
+    dim3 grid(cdiv(W, 32), cdiv(H, 8)), block(32, 8);
+    geo_backproject_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(depth, mask, cam, xyz, H, W);
+    return check_launch("mvs_geo_backproject");
+}
 
 extern "C" int mvs_geo_consistency(const float *depth_ref, const float *depth_src, const double *cam, uint8_t *mask,
                                    float *depth_reproj, float *x_src, float *y_src, float *x_rep, float *y_rep, int H, int W,

@@ -129,3 +129,24 @@ def fuse_ref_view(ref_depth_est, confidence, ref_intrinsics, ref_extrinsics, src
         out["all_srcview_geomask"] = _out(masks.bool(), as_np)
         out["all_srcview_depth_ests"] = _out(reproj, as_np)
     return out
+
+
+def backproject(depth_est_averaged, valid_points, ref_intrinsics, ref_extrinsics):
+    """World points of the valid pixels -- filter_depth, MVSNet/eval.py:293-301: returns `xyz_world.transpose((1, 0))`
+    as float32 [n_valid, 3] in the reference's order (row-major over the image).  NumPy in -> NumPy out."""
+    dev = depth_est_averaged.device if isinstance(depth_est_averaged, torch.Tensor) else _device()
+    as_np = not isinstance(depth_est_averaged, torch.Tensor)
+    d = (torch.from_numpy(np.ascontiguousarray(depth_est_averaged, dtype=np.float64)).to(dev) if as_np
+         else depth_est_averaged.to(torch.float64).contiguous())
+    m = valid_points if isinstance(valid_points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(valid_points))
+    m = m.to(dev).to(torch.uint8).contiguous()
+    if d.dim() != 2 or m.shape != d.shape:
+        raise ValueError("depth and mask must be [H, W] of equal shape")
+    H, W = d.shape
+    Kr, Er = _np64(ref_intrinsics), _np64(ref_extrinsics)
+    cam = torch.from_numpy(np.concatenate([np.linalg.inv(Kr).ravel(), np.linalg.inv(Er)[:3].ravel()])).to(dev)
+    xyz = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().mvs_geo_backproject(_p(d), _p(m), _p(cam), _p(xyz), H, W, _stream()), "mvs_geo_backproject")
+    pts = xyz[m.bool()]
+    return _out(pts, as_np)

@@ -94,3 +94,13 @@ def test_gpu_full_size_properties():
     assert bool((out["geo_mask_sum"][ok] == 10).all())
     assert torch.allclose(out["depth_est_averaged"][ok], d[ok].double(), rtol=1e-6)
     assert bool((out["final_mask"] == ok).all())
+
+
+@pytest.mark.gpu
+def test_gpu_backproject_matches_oracle():
+    from mvs_b200 import fusion
+    g, gold = cases.geo_case(), cases.golden("geo_filter")
+    ref = G.backproject(gold["depth_est_averaged"], gold["final_mask"], g["K"][0], g["E"][0])
+    pts = fusion.backproject(gold["depth_est_averaged"], gold["final_mask"], g["K"][0], g["E"][0])
+    assert pts.shape == ref.shape and pts.dtype == np.float32
+    np.testing.assert_allclose(pts, ref.astype(np.float32), rtol=2e-7, atol=1e-4)
