@@ -269,11 +269,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 // MC = CTAs per SM the register allocator must allow (old modes): 3 for layers that live on occupancy, 2 for the
 // skip layers whose epilogue keeps four rows (TMEM + skip loads) in flight
 template <bool TM, int MC>
-__global__ void __launch_bounds__(TM ? UM_THREADS_TM : UM_THREADS, MC)
+__global__ void __launch_bounds__(TM ? UM_THREADS_TM : UM_THREADS, TM ? 1 : MC)
 conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__ x, const uint4 *__restrict__ wpk,
                    const float *__restrict__ scale, const float *__restrict__ shift, const uint4 *__restrict__ skip,
                    void *__restrict__ y)
 {
+    constexpr bool kSkip = MC == 2;          // the launcher picks the <., 2> instantiations exactly when a skip tensor is given
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4 *sw = reinterpret_cast<uint4 *>(smem_raw);                 // packed weights of this Cout tile
     uint4 *sa = sw + P.weight_units + P.zero_units;                  // ring of depth slabs (after weights + zero block)
@@ -425,7 +426,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     if (!w_ok || h0 + a >= P.Ho || cb >= P.cout_chunks) return;
                     const uint32_t oidx = so + (uint32_t)a * rs32 + (uint32_t)(n0 >> 3) * vo32;
                     uint4 sk = make_uint4(0, 0, 0, 0);
-                    if (P.has_skip) sk = __ldg(sbase + oidx);
+                    if (kSkip) sk = __ldg(sbase + oidx);
                     const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
                     uint32_t pk[4];
 #pragma unroll
@@ -435,7 +436,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         v = __fadd2_rn(v, make_float2(__uint_as_float(r2[2 * e]), __uint_as_float(r2[2 * e + 1])));
                         v = __ffma2_rn(v, scl[e], shl[e]);
                         if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
-                        if (P.has_skip) {
+                        if (kSkip) {
                             v.x += __uint_as_float(sv[e] << 16);
                             v.y += __uint_as_float(sv[e] & 0xffff0000u);
                         }
@@ -772,7 +773,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 for (int e = 0; e < 4; ++e) {
                     float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), scl[e], shl[e]);
                     if (P.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); }
-                    if (P.has_skip) {
+                    if (kSkip) {
                         t.x += __uint_as_float(sv[e] << 16);
                         t.y += __uint_as_float(sv[e] & 0xffff0000u);
                     }
@@ -831,7 +832,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         sk[j] = make_uint4(0, 0, 0, 0);
                         if (a0 + j < P.n_acc) {
                             pos[j] = out_pos(a0 + j, ok[j]);
-                            if (P.has_skip && ok[j]) sk[j] = __ldg(sbase + pos[j]);
+                            if (kSkip && ok[j]) sk[j] = __ldg(sbase + pos[j]);
                             tmem_ld8_nowait(tcol0 + (uint32_t)((a0 + j) * P.n), r[j]);
                         }
                     }
@@ -850,7 +851,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         const bool live = ok && c0 < P.cout, has_hi = c0 + 8 < P.cout_chunks * 8;
                         const uint32_t base = (uint32_t)(n0 >> 3) * vo32 + pos;
                         uint4 sk_lo = make_uint4(0, 0, 0, 0), sk_hi = make_uint4(0, 0, 0, 0);
-                        if (P.has_skip && live) {
+                        if (kSkip && live) {
                             sk_lo = __ldg(sbase + base);
                             if (has_hi) sk_hi = __ldg(sbase + base + vo32);
                         }
@@ -1384,7 +1385,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
         return cudaSuccess;
     };
     cudaError_t e;
-    if (P.tmerged) e = launch(conv3d_umma_kernel<true, 1>, UM_THREADS_TM);
+    if (P.tmerged) e = skip_c8 ? launch(conv3d_umma_kernel<true, 2>, UM_THREADS_TM) : launch(conv3d_umma_kernel<true, 1>, UM_THREADS_TM);
     else if (skip_c8) e = launch(conv3d_umma_kernel<false, 2>, UM_THREADS);
     else e = launch(conv3d_umma_kernel<false, 3>, UM_THREADS);
     if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
