@@ -951,15 +951,19 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
     g.nblk = g.mode == UM_CONV_S1 ? 3 : 1;
     g.tmerged = 0; g.pad_rows = 0;
     static const int no_tmerged = getenv("MVS_UMMA_NO_TMERGED") ? atoi(getenv("MVS_UMMA_NO_TMERGED")) : 0;   // A/B knob
-    if (g.mode == UM_CONV_S1 && n_full <= 32 && !no_tmerged) {
-        // T-merged candidate: n = 8 for Cout <= 8 (N = rows*24 is padded to a multiple of 16 with 8 zero B rows),
-        // else n = Cout padded to 16.  Taken when the packed weights + a 3-deep ring of 3-row slabs fit shared memory.
-        const int n = Cout <= 8 ? 8 : n_full;
-        const int pad = n == 8 ? 8 : 0;
+    if (g.mode == UM_CONV_S1 && !no_tmerged) {
+        // T-merged candidate: n = 8 for Cout <= 8 (N = rows*24 is padded to a multiple of 16 with 8 zero B rows), else
+        // Cout tiles of n = 32 or 16 (Cout padded to 16).  Taken when the packed weights of one Cout tile + a 2-deep ring
+        // of 3-row slabs fit shared memory (Cin = 64 -> 64: four tiles of 16).
+        int n = Cout <= 8 ? 8 : (n_full > 32 ? 32 : n_full);
         const int ksteps = CH == 1 ? 2 : 3 * ((CH + 1) / 2);
-        const size_t wbytes = (size_t)ksteps * 2 * (9 * n + pad) * 16, slab3 = (size_t)3 * CH * UM_COLS * 16;
-        if (wbytes + 3 * slab3 + 4096 <= 226 * 1024 && ksteps * 9 <= UM_MAX_KSTEPS) {
-            g.tmerged = 1; g.pad_rows = pad; g.n = n; g.cout_tiles = 1; g.nblk = 9;
+        const size_t slab3 = (size_t)3 * CH * UM_COLS * 16;
+        auto wbytes_of = [&](int nn) { return (size_t)ksteps * 2 * (9 * nn + (nn == 8 ? 8 : 0)) * 16; };
+        if (n == 32 && wbytes_of(32) + 2 * slab3 + 8192 > 226 * 1024) n = 16;
+        const int pad = n == 8 ? 8 : 0;
+        const size_t wbytes = wbytes_of(n);
+        if (wbytes + 2 * slab3 + 8192 <= 226 * 1024 && ksteps * 9 <= UM_MAX_KSTEPS) {
+            g.tmerged = 1; g.pad_rows = pad; g.n = n; g.cout_tiles = Cout <= 8 ? 1 : (n_full + n - 1) / n; g.nblk = 9;
             auto add9 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1) {
                 KStep k{0, 0, 0, col, chunk, lbo, 0, {{0, 0}, {0, 0}}};
                 g.ks.push_back(k);
@@ -1064,7 +1068,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     const bool merged = g.nblk == 3;                 // stride-1 conv: kh taps merged along N
     if (g.tmerged) {
         P.Do = D; P.Ho = H; P.Wo = W;
-        P.cin_chunks = g.cin_chunks; P.cout = Cout; P.cout_chunks = (Cout + 7) / 8; P.n = g.n; P.cout_tiles = 1;
+        P.cin_chunks = g.cin_chunks; P.cout = Cout; P.cout_chunks = (Cout + 7) / 8; P.n = g.n; P.cout_tiles = g.cout_tiles;
         P.mode = g.mode; P.arr = 1; P.tmerged = 1;
         P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip;
         P.rd = 3; P.d_mul = 1;
