@@ -1359,7 +1359,10 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
         const long long target = (waves_env > 0 ? (long long)waves_env : 8LL * 2) * 148;
         long long chunks = (target + base_ctas - 1) / base_ctas;
         static const int min_steps_env = getenv("MVS_UMMA_MIN_STEPS") ? atoi(getenv("MVS_UMMA_MIN_STEPS")) : 0;
-        const int min_steps = min_steps_env > 0 ? min_steps_env : (base_ctas * (P.steps / 8 > 0 ? P.steps / 8 : 1) < 2 * 148 ? 4 : 8);
+        // layers too small to fill the GPU even with 4-step chunks (the 1/8-resolution bottleneck) go down to 2 steps
+        const int min_steps = min_steps_env > 0 ? min_steps_env
+                              : (base_ctas * (P.steps / 4 > 0 ? P.steps / 4 : 1) < 148 ? 2
+                                 : (base_ctas * (P.steps / 8 > 0 ? P.steps / 8 : 1) < 2 * 148 ? 4 : 8));
         const long long max_chunks = P.steps / min_steps > 1 ? P.steps / min_steps : 1;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
