@@ -46,6 +46,7 @@ namespace mvs {
 
 constexpr int UM_EPI_THREADS = 128;
 constexpr int UM_PROD_THREADS = 128;
+constexpr int UM_PROD_WARPS_TM = 6;      // T-merged kernel: warps 4-7 + the two issuer warps it does not use (10, 11)
 constexpr int UM_MAX_ISSUERS = 4;
 constexpr int UM_THREADS = UM_EPI_THREADS + UM_PROD_THREADS + 32 * UM_MAX_ISSUERS;
 constexpr int UM_THREADS_TM = UM_THREADS + UM_EPI_THREADS;     // T-merged kernel: + a second epilogue group (warps 12-15)
@@ -306,7 +307,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     if (tid == 32) {
         const uint32_t n_commit = (P.merged || TM) ? 1u : (uint32_t)P.n_issuers;
         // T-merged: slabs arrive by bulk copies (tx bytes) + one arrival per producer warp
-        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, TM ? UM_PROD_THREADS / 32 : UM_PROD_THREADS); mbar_init(empty + i, n_commit); }
+        for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, TM ? UM_PROD_WARPS_TM : UM_PROD_THREADS); mbar_init(empty + i, n_commit); }
         for (int i = 0; i < UM_TBUFS; ++i) { mbar_init(tfull + i, n_commit); mbar_init(tempty + i, TM ? 2 * UM_EPI_THREADS : UM_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -482,9 +483,12 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         }
         rt.flush();
     } else
-    if (warp >= 4 && warp < 8) {
-        // =========================== producers: global -> shared (cp.async) ===========================
-        const int pwarp = warp - 4;
+    if ((warp >= 4 && warp < 8) || (TM && (warp == 10 || warp == 11))) {
+        // =========================== producers: global -> shared (cp.async / bulk copies) =============
+        // (T-merged: a UBLKCP costs its issuing WARP ~300-450 clk whichever lane issues it, so the lines of a slab are
+        // spread over six warps: the four producer warps and the two issuer warps this mode leaves idle)
+        const int pwarp = warp < 8 ? warp - 4 : warp - 6;
+        constexpr int NPW = TM ? UM_PROD_WARPS_TM : UM_PROD_THREADS / 32;
         const int lines = P.rh * P.cin_chunks * P.arr;                // lines of UM_COLS 16-byte vectors per slab
         const size_t plane_in = (size_t)P.Hr * P.W;
         int pending = -1;              // slab staged (cp.async committed) but not yet published
@@ -508,7 +512,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             RoleTimer rt; rt.start(trace && tid == 128, trace, 1);
             const int c_lo = m0 == 0 ? 1 : 0;                                  // column c holds w = m0 - 1 + c
             const int c_hi = min(UM_COLS, P.W - m0 + 1);
-            const int ln = pwarp + (UM_PROD_THREADS / 32) * lane;
+            const int ln = pwarp + NPW * lane;
             const int my_row = ln / P.cin_chunks, my_chunk = ln % P.cin_chunks;
             const int my_h = h0 - 1 + my_row;
             const bool my_ok = ln < lines && my_h >= 0 && my_h < P.H && c_hi > c_lo;
@@ -533,7 +537,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 uint4 *slab = sa + (size_t)slot * P.slab_units;
                 if (!d_ok || edge_cols || edge_rows) {
                     // zero the parts no copy will write (smem slots are recycled, so this is redone per slab)
-                    for (int l2 = pwarp; l2 < lines; l2 += UM_PROD_THREADS / 32) {
+                    for (int l2 = pwarp; l2 < lines; l2 += NPW) {
                         const int h_in = h0 - 1 + l2 / P.cin_chunks;
                         const bool row_ok = d_ok && h_in >= 0 && h_in < P.H;
                         uint4 *dst = slab + (size_t)l2 * UM_COLS;
@@ -600,7 +604,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             fence_async_smem();
             mbar_arrive(full + mod_ring(pending, P.ring, P.ring_magic));
         }
-    } else if (warp >= 8 && warp < 12) {
+    } else if (warp >= 8 && warp < 12) {       // (T-merged: warps 10, 11 were taken by the producer branch above)
         // =========================== MMA issuers ======================================================
         // Up to UM_MAX_ISSUERS warps, each owning a disjoint set of accumulators (independent chains).
         // A whole warp walks its slice of the op table on warp-uniform values (kernel-parameter table,
