@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvs_b200.so")
+# MVS_B200_LIB points at an alternative build of the same C-ABI (kernel tuning experiments); default: the in-tree library
+LIB_PATH = os.environ.get("MVS_B200_LIB") or os.path.join(_HERE, "libmvs_b200.so")
 
 # flags / enums (mirror include/mvs_b200.h)
 ALIGN_CORNERS = 1
