@@ -28,9 +28,8 @@ import sys
 import threading
 import time
 
-# rank 0 prints ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints ONE JSON line on stdout: NCCL's "NCCL version ..." banner (any NCCL_DEBUG level >= VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
