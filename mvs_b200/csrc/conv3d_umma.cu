@@ -15,28 +15,34 @@
 // classes over input-resolution rows.  All of that is expressed as a per-layer table of MMA ops
 // built on the host (ConvPlan), so there is one kernel.
 //
-// CTA = one M tile of 128 w-positions x ht rows; it owns (batch, h-block, w-block, Cout-tile) and
-// walks the depth axis, so every input byte is fetched (1 + 2/ht) times from L2 and the packed
-// weights are staged once per CTA.  Warp-specialised pipeline, mbarrier-synchronised:
-//   warps 4-7   producers : cp.async (16 B, zero-fill for the halo) input depth-slabs into a ring
-//   warps 8-11  issuers   : walk the op table in the uniform datapath, one elected lane issues
-//                           tcgen05.mma -> TMEM and tcgen05.commit -> mbarrier
-//   warps 0-3   epilogue  : tcgen05.ld (32x32b) -> folded-BN affine + ReLU + skip -> C8 bf16 store
-//                           (or fp32 logits for the Cout = 1 `prob` layer)
-// The accumulators are double-buffered in TMEM (step s+1's MMAs overlap step s's epilogue) and the
-// slab ring holds one step of prefetch.
+// Two kernels (template <TM, MC>), both warp-specialised and mbarrier-synchronised; a CTA owns one M tile of 128
+// w-positions x ht rows x a chunk of the "step" axis (real H; the rows tile real D), weights staged once per CTA.
 //
-// What bounds it (ncu, profiles/): these MMAs are tiny (M128 x N16..48 x K16), so the tensor pipe is
-// limited by operand fetch -- every MMA reads a 4 KB A tile from shared memory -- and by issue rate, not
-// by math.  Hence: (i) stride-1 layers merge the three kh taps of an input row into ONE MMA of
-// N = 3*n whose accumulator columns are the three output rows it feeds (A fetched once for three rows;
-// a zero-B MMA initialises the accumulators; two issuers alternate depth steps so they never share an
-// accumulator, and the epilogue -- which has seen every earlier step complete -- releases the slabs);
-// (ii) the other layers split their accumulators over up to four issuer warps; (iii) op entries are
-// issue-ready 16-byte records in kernel-parameter (constant) space grouped by depth slab, so an MMA
-// costs one uniform load + three adds; descriptors are built by the whole warp on warp-uniform values
-// and only the instruction is predicated on an elected lane (issuing from `if (lane == 0)` makes the
-// compiler wrap every UTCHMMA in an R2UR waterfall loop; predicating inside the PTX is silently dropped).
+// (1) conv3d_umma_kernel<true, .>  -- "T-merged" mode, every stride-1 layer (conv0/2/4/6, prob; CVP's stride-1 layers):
+//   Measured cost model (tools/micro/umma_rate.cu): an M128 x N x K16 MMA costs max(N/2, 32 + N/4) clk in the tensor pipe
+//   and ~85 clk of one issuing warp, almost independent of N for N <= 80 -- and CostRegNet has Cout = 1 / 8 / 16.  So ONE
+//   MMA per (staged input row, kw group, Cin pair) carries all nine (row tap, step tap) weight blocks along N: the row
+//   taps accumulate inside the MMA (B sub-block 2 - (i - lo) lines the taps up with output rows lo..hi), the three step
+//   taps land in column blocks [row][t][n] of a PER-SLAB TMEM buffer (ring of 4), and the epilogue adds the partials of
+//   slabs s, s+1, s+2.  Every slab is read once.
+//     warps 4-7,10,11 producers : one 1-D bulk copy (cp.async.bulk + mbarrier complete_tx) per staged line; halo parts
+//                                 are zero-filled with ordinary stores on border CTAs only
+//     warps 8-9       issuers   : alternate slabs (ring and buffer count even => one waiting warp per barrier); op table
+//                                 in kernel-parameter space, descriptors built in the uniform datapath
+//     warps 0-3,12-15 epilogue  : two groups split the rows; three tcgen05.ld per 8-channel block -> sum -> folded BN +
+//                                 ReLU (+ skip) -> C8 bf16 store / fp32 logits
+// (2) conv3d_umma_kernel<false, .> -- table-driven modes for stride-2 convs (even / odd staged arrays) and transposed
+//   stride-2 convs (8 output-parity accumulators per row):
+//     warps 4-7 producers (cp.async 16 B with zero-fill, slab-invariant index math in a shared-memory line table),
+//     warps 8-11 issuers (each owns a slice of the accumulators), warps 0-3 epilogue (skip vectors prefetched before the
+//     TMEM wait, four accumulators per batch); TMEM double-buffered per step.  <false, 2>: skip layers, 2 CTAs/SM;
+//     <false, 3>: the others, 3 CTAs/SM.
+//
+// Lessons that shaped the code (DESIGN.md 4.2 has the measurements): every role is ONE warp running dependent scalar
+// code (~5 clk per instruction), so per-step bookkeeping -- runtime divisions, re-materialised 64-bit index arithmetic,
+// dynamically indexed parameter reads -- is what the pipeline waits for, not bytes or FLOPs; issuing tcgen05.mma from
+// inside `if (lane == 0)` makes the compiler wrap every UTCHMMA in an R2UR waterfall loop (use elect.sync + uniform
+// operands); a UBLKCP costs its issuing warp 300-450 clk (spread the lines over warps).
 #include <cstdlib>
 #include <vector>
 
