@@ -19,13 +19,15 @@ STAGE_SCALES = {"stage1": 4, "stage2": 2, "stage3": 1}   # CasMVSNet/models/cas_
 def cascade_hot_path(features: Sequence[Dict[str, torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
                      depth_values: torch.Tensor, cost_regularization, ndepths=(48, 32, 8),
                      depth_interals_ratio=(4, 2, 1), img_hw=None, depth_min: Optional[float] = None,
-                     depth_max: Optional[float] = None):
+                     depth_max: Optional[float] = None, stage_hook=None):
     """CascadeMVSNet.forward after feature extraction (CasMVSNet/models/cas_mvsnet.py:109-165).
 
     features: one dict per view {"stage1": [B,32,H/4,W/4], "stage2": [B,16,H/2,W/2], "stage3": [B,8,H,W]}
     proj_matrices: {"stageK": [B,N,2,4,4]};  depth_values [B,Dd] (only [0,0] and [0,-1] are used,
     exactly like the reference, cas_mvsnet.py:110-112).  `depth_min/max` may be given as Python floats
-    to skip the reference's device->host read.
+    to skip the reference's device->host read.  `stage_hook(stage_idx)`, if given, is called right before a stage first
+    touches its feature maps -- a streaming caller makes the compute stream wait there for that stage's input copy, so
+    the coarse stages run while the fine stage's (4x larger) features are still on the PCIe bus.
     Returns the reference's dict: per-stage {"depth","photometric_confidence"} + last stage at top level.
     """
     if img_hw is None:
@@ -45,6 +47,8 @@ def cascade_hot_path(features: Sequence[Dict[str, torch.Tensor]], proj_matrices:
     for stage_idx, nd in enumerate(ndepths):
         key = "stage%d" % (stage_idx + 1)
         scale = STAGE_SCALES[key]
+        if stage_hook is not None:
+            stage_hook(stage_idx)
         feats = [f[key] for f in features]
         hyp = None
         if depth is not None:
