@@ -104,3 +104,27 @@ def test_gpu_backproject_matches_oracle():
     pts = fusion.backproject(gold["depth_est_averaged"], gold["final_mask"], g["K"][0], g["E"][0])
     assert pts.shape == ref.shape and pts.dtype == np.float32
     np.testing.assert_allclose(pts, ref.astype(np.float32), rtol=2e-7, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_vs_numpy_time(capsys):
+    """cfg3 image size, 4 source views: GPU fused filter vs the NumPy restatement -- masks agree up to threshold ties, and the
+    two wall times are printed side by side (the reference's filter_depth spends seconds per view here)."""
+    import time
+    import torch
+    from mvs_b200 import fusion
+    g = cases.geo_case(n_src=4, H=1184, W=1600)
+    t0 = time.perf_counter()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s, avg, _, gm, fm = G.fuse_ref_view(g["depth"][0], g["conf"], g["K"][0], g["E"][0], g["depth"][1:], g["K"][1:], g["E"][1:])
+    cpu_s = time.perf_counter() - t0
+    d = [torch.from_numpy(x).cuda() for x in g["depth"]]
+    conf = torch.from_numpy(g["conf"]).cuda()
+    fn = lambda: fusion.fuse_ref_view(d[0], conf, g["K"][0], g["E"][0], d[1:], list(g["K"][1:]), list(g["E"][1:]))
+    out = fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); out = fn(); torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    assert (out["geo_mask_sum"].cpu().numpy() != s).mean() < 1e-4
+    assert (out["final_mask"].cpu().numpy() != fm).mean() < 1e-4
+    with capsys.disabled():
+        print(f"\n[geo filter 1184x1600, 4 sources] NumPy restatement {cpu_s:.2f} s, mvs_geo_fuse {1e3 * gpu_s:.2f} ms")

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Times the fused geometric-consistency filter (mvs_geo_fuse) at the cfg3 image size against its HBM floor and counts
-disagreements with the NumPy restatement of the reference on a small case.
+(the side-by-side time of the NumPy restatement is printed by tests/test_geo_filter.py::test_gpu_full_size_vs_numpy_time:
+only tests/ may import oracle/).
 
     python tools/prof_geo.py [--nsrc 10]
 """
@@ -8,7 +9,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -40,13 +40,8 @@ def main():
     ms = float(np.median(ts))
     # algorithmic bytes: every map read once + geo_sum (4) + depth_avg (8) + final_mask (1) written once
     nbytes = H * W * (4 * (a.nsrc + 2) + 13)
-    t0 = time.perf_counter()
-    from oracle import geo_oracle as G          # CPU restatement of the reference, for the side-by-side time only
-    with np.errstate(divide="ignore", invalid="ignore"):
-        G.fuse_ref_view(g["depth"][0], g["conf"], g["K"][0], g["E"][0], g["depth"][1:], g["K"][1:], g["E"][1:])
-    cpu_s = time.perf_counter() - t0
     print(json.dumps(dict(H=H, W=W, nsrc=a.nsrc, ms=round(ms, 4), alg_MB=round(nbytes / 1e6, 1), GBps=round(nbytes / ms / 1e6, 1),
-                          final_mask_frac=float(out["final_mask"].float().mean()), numpy_restatement_s=round(cpu_s, 2))))
+                          final_mask_frac=float(out["final_mask"].float().mean()))))
 
 
 if __name__ == "__main__":
