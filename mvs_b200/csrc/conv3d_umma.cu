@@ -109,7 +109,7 @@ struct ConvPlan {
     long long *trace;                               // profiling hook (mvs_conv3d_c8_set_trace): per-CTA role timers, or null
     int trace_ctas;
     uint32_t ring_magic;                            // (1 << 18) / ring + 1: x / ring == (x * ring_magic) >> 18 for x < 32768
-    int tmerged, buf_cols, prefetch;                // prefetch: slabs in flight per producer thread (<= ring - 1)
+    int tmerged, buf_cols;
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
@@ -174,17 +174,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-// Role timers of the profiling hook: slot k of CTA c accumulates clock64 deltas at trace[c * 16 + k].
-//   0 CTA total | 1 producer wait empty | 2 producer stage+publish | 3 issuer wait full | 4 issuer wait tempty
-//   5 issuer issue | 6 epilogue wait tfull | 7 epilogue work | 9 prologue (until roles start) | 10 steps
 // x / ring and x % ring without a hardware-less integer division (~25 dependent instructions each): exact for x < 32768
 __device__ __forceinline__ int div_ring(int x, uint32_t magic) { return (int)(((uint32_t)x * magic) >> 18); }
 __device__ __forceinline__ int mod_ring(int x, int ring, uint32_t magic) { return x - div_ring(x, magic) * ring; }
@@ -231,20 +220,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
-// wait until at most n (0..6) of the most recently committed groups are still pending
-__device__ __forceinline__ void cp_async_wait_dyn(int n)
-{
-    switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    default: cp_async_wait<6>(); break;
-    }
-}
-
 // TMEM loads WITHOUT the wait: issue several, then tmem_wait_ld() once.
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16])
 {
@@ -1102,7 +1077,6 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         }
         if (!best) return false;
         P.ht = best; P.ring = best_ring; P.rh = P.ht + 2;
-        P.prefetch = P.ring - 1 < 5 ? P.ring - 1 : 5;
         P.slab_units = P.rh * g.cin_chunks * UM_COLS;
         P.buf_cols = round_up(P.ht * n3 + g.pad_rows, 16);
         P.zero_units = 2 * P.buf_cols;
