@@ -251,7 +251,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 // MC = CTAs per SM the register allocator must allow (old modes): 3 for layers that live on occupancy, 2 for the
 // skip layers whose epilogue keeps four rows (TMEM + skip loads) in flight
 template <bool TM, int MC>
-__global__ void __launch_bounds__(TM ? UM_THREADS_TM : UM_THREADS, TM ? 1 : MC)
+__global__ void __launch_bounds__(TM ? UM_THREADS_TM : (MC == 2 ? UM_THREADS + UM_EPI_THREADS : UM_THREADS), TM ? 1 : MC)
 conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__ x, const uint4 *__restrict__ wpk,
                    const float *__restrict__ scale, const float *__restrict__ shift, const uint4 *__restrict__ skip,
                    void *__restrict__ y)
@@ -289,13 +289,13 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const uint32_t n_commit = (P.merged || TM) ? 1u : (uint32_t)P.n_issuers;
         // T-merged: slabs arrive by bulk copies (tx bytes) + one arrival per producer warp
         for (int i = 0; i < P.ring; ++i) { mbar_init(full + i, TM ? UM_PROD_WARPS_TM : UM_PROD_THREADS); mbar_init(empty + i, n_commit); }
-        for (int i = 0; i < UM_TBUFS; ++i) { mbar_init(tfull + i, n_commit); mbar_init(tempty + i, TM ? 2 * UM_EPI_THREADS : UM_EPI_THREADS); }
+        for (int i = 0; i < UM_TBUFS; ++i) { mbar_init(tfull + i, n_commit); mbar_init(tempty + i, (TM || MC == 2) ? 2 * UM_EPI_THREADS : UM_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     {   // weights: staged once per CTA
         const uint4 *src = wpk + (size_t)ct * P.weight_units;
-        for (int i = tid; i < P.weight_units; i += (TM ? UM_THREADS_TM : UM_THREADS)) sw[i] = __ldg(src + i);
-        for (int i = tid; i < P.zero_units; i += (TM ? UM_THREADS_TM : UM_THREADS)) sw[P.weight_units + i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < P.weight_units; i += blockDim.x) sw[i] = __ldg(src + i);
+        for (int i = tid; i < P.zero_units; i += blockDim.x) sw[P.weight_units + i] = make_uint4(0, 0, 0, 0);
     }
     if (tid < P.n) {   // epilogue affine of this Cout tile; padded channels get (0, 0) so they store 0
         const int c = ct * P.n + tid;
@@ -316,7 +316,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         // producer line table: everything about a staged line that does not depend on the slab
         const int lines = P.rh * P.cin_chunks * P.arr;
         const size_t plane_in = (size_t)P.Hr * P.W;
-        for (int ln = tid; ln < lines; ln += UM_THREADS) {
+        for (int ln = tid; ln < lines; ln += blockDim.x) {
             const int chunk = (ln / P.arr) % P.cin_chunks, r = ln / (P.arr * P.cin_chunks);
             const int h_in = P.h_mul * h0 + P.h_base + r;
             unsigned long long v = ~0ull;
@@ -717,10 +717,14 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 __syncwarp();
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 4 || (MC == 2 && warp >= 12)) {
         // =========================== epilogue: TMEM -> registers -> global ============================
-        const int m = warp * 32 + lane;                               // row of the M tile owned by this thread
-        const uint32_t lane_base = taddr + ((uint32_t)(warp * 32) << 16);
+        // (skip variant <false, 2>: a second group of four warps, 12-15, takes every other batch of accumulators -- the
+        // transposed layers are epilogue-bound: 16 accumulators x (TMEM load, skip load, affine, store) per step)
+        constexpr int NEG = MC == 2 ? 2 : 1;
+        const int eg = warp >= 12 ? 1 : 0, ew = warp & 3;
+        const int m = ew * 32 + lane;                                 // row of the M tile owned by this thread
+        const uint32_t lane_base = taddr + ((uint32_t)(ew * 32) << 16);
         const int ow_thread = P.w_mul * (m0 + m);                     // + wadd = output w
         const uint32_t epi_step_stride = (uint32_t)(P.swap ? (size_t)P.Wo : (size_t)P.Hor * P.Wo) * (uint32_t)P.od_mul;
         // 64-bit bases once per thread, 32-bit voxel offsets in the loops (the launcher checks the volume fits 31 bits)
@@ -741,7 +745,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const int buf = step & 1, use = step >> 1;
             mbar_wait(tfull + buf, (uint32_t)use & 1u);
             tc_fence_after();
-            if (P.merged && tid == 0) {
+            if (P.merged && tid == 0) {      // (merged mode never has MC == 2 groups competing: it is T-merged or skip-free)
                 // steps complete in order as seen from here (we waited on every earlier tfull), so no MMA of
                 // any step <= `step` still reads the slabs this step retires
                 for (int k = 0; k < P.d_mul; ++k) mbar_arrive(empty + mod_ring(P.d_mul * step + k, P.ring, P.ring_magic));
@@ -785,7 +789,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             };
             if (P.out_f32) {
                 // `prob` layer: one real channel -> fp32 logits; four rows' single-column loads per wait
-                for (int a0 = 0; a0 < P.n_acc; a0 += 4) {
+                for (int a0 = 4 * eg; a0 < P.n_acc; a0 += 4 * NEG) {
                     uint32_t r[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -806,7 +810,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 // one 8-channel block per row: x8 loads, two rows in flight per wait
                 // four rows per batch: positions, skip loads and TMEM loads are issued together, one wait
                 constexpr int EB = MC >= 3 ? 2 : 4;
-                for (int a0 = 0; a0 < P.n_acc; a0 += EB) {
+                for (int a0 = EB * eg; a0 < P.n_acc; a0 += EB * NEG) {
                     uint32_t r[EB][8];
                     uint32_t pos[EB];
                     bool ok[EB];
@@ -827,7 +831,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         if (ok[j]) store_with(r[j], pos[j], sk[j], sc2, sh2);
                 }
             } else {
-                for (int a = 0; a < P.n_acc; ++a) {
+                for (int a = eg; a < P.n_acc; a += NEG) {
                     bool ok;
                     const uint32_t pos = out_pos(a, ok);
                     for (int n0 = 0; n0 < P.n; n0 += 16) {
@@ -1377,7 +1381,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     };
     cudaError_t e;
     if (P.tmerged) e = skip_c8 ? launch(conv3d_umma_kernel<true, 2>, UM_THREADS_TM) : launch(conv3d_umma_kernel<true, 1>, UM_THREADS_TM);
-    else if (skip_c8) e = launch(conv3d_umma_kernel<false, 2>, UM_THREADS);
+    else if (skip_c8) e = launch(conv3d_umma_kernel<false, 2>, UM_THREADS + UM_EPI_THREADS);
     else e = launch(conv3d_umma_kernel<false, 3>, UM_THREADS);
     if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     return check_launch("mvs_conv3d_c8_fwd");
