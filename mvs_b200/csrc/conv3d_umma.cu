@@ -188,6 +188,21 @@ struct RoleTimer {          // accumulates in registers (a global read-modify-wr
     __device__ __forceinline__ void flush() { if (p) { p[k0] = a0; p[k0 + 1] = a1; if (k0 == 3) p[k0 + 2] = a2; } }
 };
 
+// The table-driven kernels run at 56 / 64 registers: their role timers exist only in -DUM_TRACE_OLD=1 diagnostic builds
+// (tools/prof_conv_trace.py with MVS_B200_LIB pointing at such a build); in the shipped build they compile to nothing.
+#ifndef UM_TRACE_OLD
+#define UM_TRACE_OLD 0
+#endif
+#if UM_TRACE_OLD
+using RoleTimerOld = RoleTimer;
+#else
+struct RoleTimerOld {
+    __device__ __forceinline__ void start(bool, long long *, int) {}
+    __device__ __forceinline__ void lap(int) {}
+    __device__ __forceinline__ void flush() {}
+};
+#endif
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
@@ -538,7 +553,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 rt.lap(2);
             }
             rt.flush();
-        } else
+        } else {
+        RoleTimerOld rto; rto.start(trace && tid == 128, trace, 1);       // old-mode producer: 1 wait empty | 2 stage + publish
         for (int i = 0; i < n_slabs; ++i) {
             const int q = div_ring(i, P.ring_magic), slot = i - q * P.ring;
             if (q >= 1) {
@@ -550,7 +566,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     mbar_arrive(full + mod_ring(pending, P.ring, P.ring_magic));
                     pending = -1;
                 }
+                rto.lap(2);
                 mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
+                rto.lap(1);
             }
             const int d_in = P.d_base + P.d_mul * step_begin + i;
             const bool d_ok = d_in >= 0 && d_in < P.D;
@@ -579,11 +597,14 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 mbar_arrive(full + mod_ring(pending, P.ring, P.ring_magic));
             }
             pending = i;
+            rto.lap(2);
         }
+        rto.flush();
         if (pending >= 0) {
             cp_async_wait<0>();
             fence_async_smem();
             mbar_arrive(full + mod_ring(pending, P.ring, P.ring_magic));
+        }
         }
     } else if (warp >= 8 && warp < 12) {       // (T-merged: warps 10, 11 were taken by the producer branch above)
         // =========================== MMA issuers ======================================================
@@ -663,6 +684,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const int step0 = P.merged ? iss : 0, dstep = P.merged ? P.n_issuers : 1;
             const int tbl = P.merged ? 0 : iss;
             int waited = 0;
+            RoleTimerOld rti; rti.start(trace && lane == 0 && iss == 0, trace, 3);
             for (int step = step0; step < nsteps; step += dstep) {
                 const int first = P.d_mul * step;
                 // only slabs this step reads: an issuer that skips steps must not test the parity of a
@@ -673,8 +695,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     mbar_wait(full + (waited - wq * P.ring), (uint32_t)wq & 1u);
                     ++waited;
                 }
+                rti.lap(3);
                 const int buf = step & 1, use = step >> 1;
                 if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
+                rti.lap(4);
                 tc_fence_after();
                 const uint32_t tbase = taddr + (uint32_t)(buf * P.acc_cols);
                 // ops are grouped by the depth slab they read, so the slab base is loop-invariant and an op
@@ -715,7 +739,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     umma_commit(tfull + buf);
                 }
                 __syncwarp();
+                rti.lap(5);
             }
+            rti.flush();
         }
     } else if (warp < 4 || (MC == 2 && warp >= 12)) {
         // =========================== epilogue: TMEM -> registers -> global ============================
@@ -741,9 +767,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             sc2[e] = make_float2(s_scale[2 * e], s_scale[2 * e + 1]);
             sh2[e] = make_float2(s_shift[2 * e], s_shift[2 * e + 1]);
         }
+        RoleTimerOld rte; rte.start(trace && tid == 0, trace, 6);      // old-mode epilogue: 6 wait tfull | 7 work
         for (int step = 0; step < nsteps; ++step) {
             const int buf = step & 1, use = step >> 1;
             mbar_wait(tfull + buf, (uint32_t)use & 1u);
+            rte.lap(6);
             tc_fence_after();
             if (P.merged && tid == 0) {      // (merged mode never has MC == 2 groups competing: it is T-merged or skip-free)
                 // steps complete in order as seen from here (we waited on every earlier tfull), so no MMA of
@@ -857,7 +885,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             }
             tc_fence_before();         // this thread's TMEM reads are complete (tcgen05.wait::ld) ...
             mbar_arrive(tempty + buf); // ... so the issuer may overwrite the buffer
+            rte.lap(7);
         }
+        rte.flush();
     }
     tc_fence_before();
     __syncthreads();

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-role timers of the T-merged UMMA conv (mvs_conv3d_c8_set_trace): where a CTA's time goes.
+"""Per-role timers of the UMMA conv kernels (mvs_conv3d_c8_set_trace): where a CTA's time goes.
 
     python tools/prof_conv_trace.py [--stages 1,2,3] [--layers conv0,prob]
 """
@@ -38,7 +38,9 @@ def main():
             x = torch.randn(1, (cin + 7) // 8, D, H, W, 8, device=dev).bfloat16()
             wt = torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3), device=dev) / (27 * cin) ** 0.5
             pk = ops.pack_conv_weights(wt, stride, tr)
-            fn = lambda: ops.conv3d_c8(x, pk, cin, cout, None, None, None, stride, tr, cout != 1)
+            y0 = ops.conv3d_c8(x, pk, cin, cout, None, None, None, stride, tr, cout != 1)
+            sk = torch.zeros_like(y0) if has_skip else None
+            fn = lambda: ops.conv3d_c8(x, pk, cin, cout, None, None, sk, stride, tr, cout != 1)
             fn(); fn()
             buf = torch.zeros(a.ctas * 16, dtype=torch.int64, device=dev)
             lib.mvs_conv3d_c8_set_trace(buf.data_ptr(), a.ctas)
