@@ -44,6 +44,7 @@ extern "C" {
 #define MVS_BLEND_BF16 64       /* C8 builder: bilinear blend in packed bf16x2 (sums / variance stay fp32) */
 #define MVS_FAST_COORDS 128     /* mvs_warp_taps: probe the C8 builder's division-free-call tap arithmetic */
 #define MVS_FEAT_F16 256        /* C8 builder: feature maps are fp16 C8 (mvs_pack_c8h); blend in packed fp16  */
+#define MVS_WARP_NO_TMA 512     /* C8 builder: force the L1-gather kernel (default for fp16 maps: TMA-staged boxes) */
 
 /* depth_mode */
 #define MVS_DEPTH_PLANE 0       /* depth [B,D]       MVSNet/models/module.py:46                   */
@@ -133,8 +134,9 @@ int mvs_conv3d_fwd(const float *x, const float *w, const float *scale, const flo
                    const float *skip, float *y, int B, int Cin, int Cout, int D, int H, int W,
                    int stride, int transposed, int flags, void *stream);
 
-/* Fast variant: C8 bf16 activations, tcgen05 (UMMA) implicit GEMM with TMA-staged bricks and a
- * TMEM accumulator; weights pre-packed by mvs_conv3d_c8_pack_weights.  y is C8 bf16, or fp32
+/* Fast variant: C8 bf16 activations, tcgen05 (UMMA) implicit GEMM, operands staged in shared memory by the TMA engine
+ * (1-D bulk copies per staged line in the stride-1 layers, cp.async in the stride-2 / transposed layers), TMEM
+ * accumulators; weights pre-packed by mvs_conv3d_c8_pack_weights.  y is C8 bf16, or fp32
  * [B,D,H,W] when Cout == 1 (the `prob` layer). */
 int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stride, int transposed);
 int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride,

@@ -21,6 +21,7 @@ INPUT_IS_PROB = 32
 BLEND_BF16 = 64
 FAST_COORDS = 128
 FEAT_F16 = 256
+WARP_NO_TMA = 512
 DEPTH_PLANE = 0
 DEPTH_PIXEL = 1
 F32 = 0

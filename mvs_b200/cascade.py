@@ -7,7 +7,6 @@ from __future__ import annotations
 from typing import Dict, List, Optional, Sequence
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from .modules import stage_forward, cas_relative_poses
@@ -50,29 +49,21 @@ def cascade_hot_path(features: Sequence[Dict[str, torch.Tensor]], proj_matrices:
         if stage_hook is not None:
             stage_hook(stage_idx)
         feats = [f[key] for f in features]
-        hyp = None
+        fh, fw = feats[0].shape[2:4]           # NCHW [B,C,h,w] and C8 [B,CB,h,w,8] alike
+        if (fh, fw) != (H // scale, W // scale):
+            raise ValueError(f"{key}: feature maps are {fh}x{fw} but img_hw={H}x{W} at scale {scale} gives "
+                             f"{H // scale}x{W // scale} (the reference fails with a shape error here, cas_mvsnet.py:150)")
         if depth is not None:
             # bilinear up-sampling + get_depth_range_samples + trilinear resampling (cas_mvsnet.py:129-151), fused
-            hyp = ops.cas_hypotheses(depth.detach(), (H, W), (H // scale, W // scale), nd,
-                                     depth_interals_ratio[stage_idx] * depth_interval)
-            samples = None
+            hyp = ops.cas_hypotheses(depth.detach(), (H, W), (fh, fw), nd, depth_interals_ratio[stage_idx] * depth_interval)
         else:
-            # first stage: uniform planes between depth_values[:,0] and [:, -1] (module.py:509-517)
+            # first stage: uniform planes between depth_values[:,0] and [:, -1] (module.py:509-517).  The reference
+            # repeats them to [B,D,H,W] at FULL resolution (364 MB at 1600x1184) and trilinearly resamples them to the
+            # stage extent (cas_mvsnet.py:150-151); resampling a plane-uniform volume at the same D returns the same
+            # constants (probed bitwise), so the [B,D] planes go to the kernel directly (MVS_DEPTH_PLANE).
             lo, hi = depth_values[:, 0], depth_values[:, -1]
             step = (hi - lo) / (nd - 1)
-            planes = lo.unsqueeze(1) + torch.arange(0, nd, device=lo.device, dtype=lo.dtype).reshape(1, -1) * step.unsqueeze(1)
-            samples = None
-        if hyp is not None:
-            pass
-        elif samples is None:
-            # The reference repeats the planes to [B,D,H,W] at FULL resolution (364 MB at 1600x1184)
-            # and trilinearly resamples them to the stage extent (cas_mvsnet.py:150-151); resampling a
-            # plane-uniform volume at the same D returns the same constants (probed bitwise, SURVEY.md
-            # §7.3-7), so the [B,D] planes go to the kernel directly (MVS_DEPTH_PLANE).
-            hyp = planes
-        else:
-            hyp = F.interpolate(samples.unsqueeze(1), [nd, H // scale, W // scale], mode="trilinear",
-                                align_corners=False).squeeze(1)
+            hyp = lo.unsqueeze(1) + torch.arange(0, nd, device=lo.device, dtype=lo.dtype).reshape(1, -1) * step.unsqueeze(1)
         reg = cost_regularization if not isinstance(cost_regularization, (list, tuple, torch.nn.ModuleList)) \
             else cost_regularization[stage_idx]
         assert len(feats) == proj_matrices[key].shape[1], "Different number of images and projection matrices"

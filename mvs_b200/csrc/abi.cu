@@ -8,6 +8,19 @@ std::string &last_error_ref()
     return s;
 }
 std::atomic<long long> g_launches{0};
+
+int sm_count()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 }  // namespace mvs
 
 extern "C" int mvs_version(void) { return 100; }   // 0.1.0

@@ -36,6 +36,8 @@ inline int check_launch(const char *what)
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+int sm_count();        // multiProcessorCount of the current device, queried once per device (abi.cu); 148 when unknown
+
 struct SrcPtrs {
     const void *p[MVS_MAX_SRC];
 };

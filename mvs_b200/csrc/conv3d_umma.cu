@@ -1374,13 +1374,14 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     {
         const long long base_ctas = (long long)cdiv(m_ext, 128) * P.row_blocks * B * P.cout_tiles;
         static const int waves_env = getenv("MVS_UMMA_WAVES") ? atoi(getenv("MVS_UMMA_WAVES")) : 0;   // tuning knob
-        const long long target = (waves_env > 0 ? (long long)waves_env : 8LL * 2) * 148;
+        const int n_sm = sm_count();
+        const long long target = (waves_env > 0 ? (long long)waves_env : 8LL * 2) * n_sm;
         long long chunks = (target + base_ctas - 1) / base_ctas;
         static const int min_steps_env = getenv("MVS_UMMA_MIN_STEPS") ? atoi(getenv("MVS_UMMA_MIN_STEPS")) : 0;
         // layers too small to fill the GPU even with 4-step chunks (the 1/8-resolution bottleneck) go down to 2 steps
         const int min_steps = min_steps_env > 0 ? min_steps_env
-                              : (base_ctas * (P.steps / 4 > 0 ? P.steps / 4 : 1) < 148 ? 2
-                                 : (base_ctas * (P.steps / 8 > 0 ? P.steps / 8 : 1) < 2 * 148 ? 4 : 8));
+                              : (base_ctas * (P.steps / 4 > 0 ? P.steps / 4 : 1) < n_sm ? 2
+                                 : (base_ctas * (P.steps / 8 > 0 ? P.steps / 8 : 1) < 2 * n_sm ? 4 : 8));
         const long long max_chunks = P.steps / min_steps > 1 ? P.steps / min_steps : 1;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
@@ -1388,7 +1389,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
         if (P.tmerged && waves_env == 0) {
             // every CTA stages steps + 2 slabs and pays a pipeline fill (~2 steps) before its first store: pick the
             // chunking that minimises waves x (steps per CTA + 4)
-            const long long slots = 148LL * (UM_TBUFS * P.buf_cols <= 256 && smem <= 112 * 1024 ? 2 : 1);
+            const long long slots = (long long)n_sm * (UM_TBUFS * P.buf_cols <= 256 && smem <= 112 * 1024 ? 2 : 1);
             long long best_cost = -1;
             for (int c = 1; c <= P.steps; ++c) {
                 const int spc = cdiv(P.steps, c);

@@ -27,23 +27,24 @@ struct GeoSrcs {
 
 __device__ __forceinline__ double dot3(const double *m, double a, double b, double c)
 {
-    return fma(m[2], c, fma(m[1], b, m[0] * a));
+    return fma(m[2], c, fma(m[1], b, __dmul_rn(m[0], a)));
 }
 __device__ __forceinline__ double dot4h(const double *m, double a, double b, double c)     // (a, b, c, 1)
 {
-    return fma(m[3], 1.0, fma(m[2], c, fma(m[1], b, m[0] * a)));
+    return fma(m[3], 1.0, fma(m[2], c, fma(m[1], b, __dmul_rn(m[0], a))));
 }
 
 __device__ __forceinline__ float remap_bilinear(const float *__restrict__ src, int H, int W, float x, float y)
 {
-    const float xs = x * 32.0f, ys = y * 32.0f;
+    const float xs = __fmul_rn(x, 32.0f), ys = __fmul_rn(y, 32.0f);
     // cvRound of a non-finite / out-of-int-range value is the x86 "integer indefinite" INT_MIN: far outside => 0
     if (!(fabsf(xs) < 2147483648.0f) || !(fabsf(ys) < 2147483648.0f)) return 0.0f;
     const int sx = __float2int_rn(xs), sy = __float2int_rn(ys);
     const int ix = sx >> 5, iy = sy >> 5;
     const float fx = (float)(sx & 31) * (1.0f / 32.0f), fy = (float)(sy & 31) * (1.0f / 32.0f);
-    const float w0 = __fmul_rn(1.0f - fy, 1.0f - fx), w1 = __fmul_rn(1.0f - fy, fx);
-    const float w2 = __fmul_rn(fy, 1.0f - fx), w3 = __fmul_rn(fy, fx);
+    const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy);
+    const float w0 = __fmul_rn(gy, gx), w1 = __fmul_rn(gy, fx);
+    const float w2 = __fmul_rn(fy, gx), w3 = __fmul_rn(fy, fx);
     const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
     const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
     const float t0 = (x0 && y0) ? __ldg(src + (size_t)iy * W + ix) : 0.0f;
@@ -63,26 +64,26 @@ __device__ __forceinline__ GeoOut geo_pixel(const double *__restrict__ cam, cons
 {
     const double *Kri = cam, *Trs = cam + 9, *Ks = cam + 21, *Ksi = cam + 30, *Tsr = cam + 39, *Kr = cam + 51;
     const double d = (double)d_ref;
-    const double px = (double)x * d, py = (double)y * d, pz = 1.0 * d;                 // vstack((x, y, 1)) * depth
+    const double px = __dmul_rn((double)x, d), py = __dmul_rn((double)y, d), pz = d;   // vstack((x, y, 1)) * depth
     const double rx = dot3(Kri, px, py, pz), ry = dot3(Kri + 3, px, py, pz), rz = dot3(Kri + 6, px, py, pz);
     const double sx = dot4h(Trs, rx, ry, rz), sy = dot4h(Trs + 4, rx, ry, rz), sz = dot4h(Trs + 8, rx, ry, rz);
     const double kx = dot3(Ks, sx, sy, sz), ky = dot3(Ks + 3, sx, sy, sz), kz = dot3(Ks + 6, sx, sy, sz);
-    const double xs = kx / kz, ys = ky / kz;
+    const double xs = __ddiv_rn(kx, kz), ys = __ddiv_rn(ky, kz);
     GeoOut o;
     o.x_src = (float)xs;
     o.y_src = (float)ys;
     const float sampled = remap_bilinear(depth_src, H, W, o.x_src, o.y_src);
     const double sd = (double)sampled;
-    const double qx = xs * sd, qy = ys * sd, qz = 1.0 * sd;                            // vstack((xy_src, 1)) * sampled
+    const double qx = __dmul_rn(xs, sd), qy = __dmul_rn(ys, sd), qz = sd;              // vstack((xy_src, 1)) * sampled
     const double ux = dot3(Ksi, qx, qy, qz), uy = dot3(Ksi + 3, qx, qy, qz), uz = dot3(Ksi + 6, qx, qy, qz);
     const double vx = dot4h(Tsr, ux, uy, uz), vy = dot4h(Tsr + 4, ux, uy, uz), vz = dot4h(Tsr + 8, ux, uy, uz);
     o.depth_reproj = (float)vz;
     const double wx = dot3(Kr, vx, vy, vz), wy = dot3(Kr + 3, vx, vy, vz), wz = dot3(Kr + 6, vx, vy, vz);
-    o.x_rep = (float)(wx / wz);
-    o.y_rep = (float)(wy / wz);
+    o.x_rep = (float)__ddiv_rn(wx, wz);
+    o.y_rep = (float)__ddiv_rn(wy, wz);
     // dist in float64 from the float32-cast reprojection (x2d_reprojected - x_ref promotes to float64)
     const double dx = (double)o.x_rep - (double)x, dy = (double)o.y_rep - (double)y;
-    const double dist = sqrt(dx * dx + dy * dy);
+    const double dist = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));    // NumPy: two rounded squares, one add (no FMA contraction)
     const float rel = __fdiv_rn(fabsf(__fsub_rn(o.depth_reproj, d_ref)), d_ref);      // float32 throughout
     o.mask = (dist < dist_thresh) && (rel < rel_thresh);
     return o;
@@ -136,7 +137,7 @@ geo_fuse_kernel(const float *__restrict__ depth_ref, const float *__restrict__ c
     }
     acc = __fadd_rn(acc, d_ref);
     if (geo_sum) geo_sum[i] = cnt;
-    if (depth_avg) depth_avg[i] = (double)acc / (double)(cnt + 1);           // float32 / int32 promotes to float64
+    if (depth_avg) depth_avg[i] = __ddiv_rn((double)acc, (double)(cnt + 1));           // float32 / int32 promotes to float64
     if (final_mask) final_mask[i] = (cnt >= min_views && __ldg(conf + i) > conf_thresh) ? 1 : 0;
 }
 
@@ -157,7 +158,7 @@ geo_backproject_kernel(const double *__restrict__ depth, const uint8_t *__restri
     float ox = __int_as_float(0x7fc00000), oy = ox, oz = ox;
     if (!mask || mask[i]) {
         const double d = depth[i];
-        const double px = (double)x * d, py = (double)y * d, pz = 1.0 * d;
+        const double px = __dmul_rn((double)x, d), py = __dmul_rn((double)y, d), pz = d;
         const double rx = dot3(s_cam, px, py, pz), ry = dot3(s_cam + 3, px, py, pz), rz = dot3(s_cam + 6, px, py, pz);
         ox = (float)dot4h(s_cam + 9, rx, ry, rz);
         oy = (float)dot4h(s_cam + 13, rx, ry, rz);

@@ -1,0 +1,218 @@
+"""The caller side of the hot path: CasMVSNet's 2D FPN feature extractor and the whole
+`CascadeMVSNet` model behind the reference's names, state-dict keys and call signature, so that a driver can hand the
+SAME host inputs the reference takes -- images + projection matrices + depth range (cas_mvsnet.py:109-118) -- and get
+the reference's output dict back.
+
+BASELINE.json's north_star keeps the 2D extractor in PyTorch; what is built here is the hand-off:
+  * `FeatureNet` (CasMVSNet/models/module.py:304-405, arch_mode "fpn") with the reference's exact sub-module tree
+    (conv0.0.conv / conv0.0.bn ... out1, inner1, inner2, out2, out3) so reference checkpoints load with strict=True;
+  * mode "strict": the reference's op sequence in fp32 (NCHW) -- parity mode;
+  * mode "fast": eval-mode BatchNorm folded into the convolution weights, fp16 channels-last activations, ALL N views of
+    a reference view in ONE batched call (as MVSNet_pl/models/mvsnet.py:85-88 does) instead of a Python loop over views
+    (cas_mvsnet.py:115-118), and the stage outputs emitted directly in the builder's C8H layout [B,C/8,h,w,8] fp16:
+    a channels-last map with C = 8 IS C8H (no repack); C = 16 / 32 need one channel-block transpose;
+  * uint8 images are accepted and normalised on the device exactly as the loader does on the host
+    (CasMVSNet/datasets/general_eval.py:81-86: float32(u8) / 255): 4x fewer bytes over PCIe, identical fp32 values.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import modules
+from .cascade import cascade_hot_path
+
+
+class Conv2d(nn.Module):
+    """Parameter holder with the reference's keys ``conv.weight[, conv.bias], bn.*`` (CasMVSNet/models/module.py:26-66)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, bias=(not bn), **kwargs)
+        self.kernel_size, self.stride = kernel_size, stride
+        self.bn = nn.BatchNorm2d(out_channels, momentum=bn_momentum) if bn else None
+        self.relu = relu
+
+    def forward(self, x):           # the reference's own sequence (strict mode / training)
+        x = self.conv(x)
+        if self.bn is not None:
+            x = self.bn(x)
+        if self.relu:
+            x = F.relu(x, inplace=True)
+        return x
+
+
+def _fold(block: Conv2d, dtype, channels_last):
+    """conv + eval BatchNorm -> (weight', bias') in `dtype`; cached until a parameter / buffer changes."""
+    tensors = [block.conv.weight] + ([block.conv.bias] if block.conv.bias is not None else [])
+    if block.bn is not None:
+        tensors += [block.bn.weight, block.bn.bias, block.bn.running_mean, block.bn.running_var]
+    key = (dtype, channels_last) + tuple((t.data_ptr(), t._version) for t in tensors)
+    cached = getattr(block, "_mvs_fold", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    with torch.no_grad():
+        w = block.conv.weight.double()
+        b = block.conv.bias.double() if block.conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device)
+        if block.bn is not None:
+            s = block.bn.weight.double() / torch.sqrt(block.bn.running_var.double() + block.bn.eps)
+            w = w * s.view(-1, 1, 1, 1)
+            b = (b - block.bn.running_mean.double()) * s + block.bn.bias.double()
+        w = w.to(dtype)
+        if channels_last:
+            w = w.contiguous(memory_format=torch.channels_last)
+        b = b.to(dtype)
+    block._mvs_fold = (key, w, b)
+    return w, b
+
+
+def _plain(conv: nn.Conv2d, dtype, channels_last):
+    key = (dtype, channels_last, conv.weight.data_ptr(), conv.weight._version,
+           None if conv.bias is None else (conv.bias.data_ptr(), conv.bias._version))
+    cached = getattr(conv, "_mvs_cast", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    with torch.no_grad():
+        w = conv.weight.to(dtype)
+        if channels_last:
+            w = w.contiguous(memory_format=torch.channels_last)
+        b = None if conv.bias is None else conv.bias.to(dtype)
+    conv._mvs_cast = (key, w, b)
+    return w, b
+
+
+def to_c8h(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,h,w] fp16 channels-last (C % 8 == 0) -> C8H [B,C/8,h,w,8] fp16 contiguous.  C == 8: a view, no copy."""
+    B, C, h, w = x.shape
+    if x.dtype != torch.float16 or C % 8:
+        raise ValueError("to_c8h takes fp16 maps with a multiple of 8 channels")
+    nhwc = x.permute(0, 2, 3, 1)
+    if not nhwc.is_contiguous():
+        nhwc = nhwc.contiguous()
+    if C == 8:
+        return nhwc.view(B, 1, h, w, 8)
+    return nhwc.view(B, h, w, C // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+
+
+class FeatureNet(nn.Module):
+    """CasMVSNet/models/module.py:304-405 with arch_mode="fpn" (the model's default, cas_mvsnet.py:72,100)."""
+
+    def __init__(self, base_channels=8, num_stage=3, stride=4, arch_mode="fpn", mode="strict"):
+        super().__init__()
+        if arch_mode != "fpn" or num_stage != 3:
+            raise NotImplementedError("mvs_b200.FeatureNet mirrors the fpn / 3-stage extractor CascadeMVSNet constructs")
+        self.arch_mode, self.stride, self.base_channels, self.num_stage, self.mode = arch_mode, stride, base_channels, num_stage, mode
+        b = base_channels
+        self.conv0 = nn.Sequential(Conv2d(3, b, 3, 1, padding=1), Conv2d(b, b, 3, 1, padding=1))
+        self.conv1 = nn.Sequential(Conv2d(b, b * 2, 5, stride=2, padding=2), Conv2d(b * 2, b * 2, 3, 1, padding=1),
+                                   Conv2d(b * 2, b * 2, 3, 1, padding=1))
+        self.conv2 = nn.Sequential(Conv2d(b * 2, b * 4, 5, stride=2, padding=2), Conv2d(b * 4, b * 4, 3, 1, padding=1),
+                                   Conv2d(b * 4, b * 4, 3, 1, padding=1))
+        self.out1 = nn.Conv2d(b * 4, b * 4, 1, bias=False)
+        self.out_channels = [4 * b]
+        final_chs = b * 4
+        self.inner1 = nn.Conv2d(b * 2, final_chs, 1, bias=True)
+        self.inner2 = nn.Conv2d(b * 1, final_chs, 1, bias=True)
+        self.out2 = nn.Conv2d(final_chs, b * 2, 3, padding=1, bias=False)
+        self.out3 = nn.Conv2d(final_chs, b, 3, padding=1, bias=False)
+        self.out_channels += [b * 2, b]
+
+    # -- strict: the reference's forward, op for op (module.py:366-405) ------------------------------------------
+    def _forward_strict(self, x):
+        if x.is_cuda and not self.training:      # parity mode means fp32 arithmetic: no TF32 inside cuDNN
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self._reference_sequence(x)
+        return self._reference_sequence(x)
+
+    def _reference_sequence(self, x):
+        conv0 = self.conv0(x)
+        conv1 = self.conv1(conv0)
+        conv2 = self.conv2(conv1)
+        intra_feat = conv2
+        outputs = {"stage1": self.out1(intra_feat)}
+        intra_feat = F.interpolate(intra_feat, scale_factor=2, mode="nearest") + self.inner1(conv1)
+        outputs["stage2"] = self.out2(intra_feat)
+        intra_feat = F.interpolate(intra_feat, scale_factor=2, mode="nearest") + self.inner2(conv0)
+        outputs["stage3"] = self.out3(intra_feat)
+        return outputs
+
+    # -- fast: folded BN, fp16 channels-last -----------------------------------------------------------------------
+    def _forward_fast(self, x):
+        dt = torch.float16
+        x = x.to(dt).contiguous(memory_format=torch.channels_last)
+
+        def seq(blocks, t):
+            for blk in blocks:
+                w, b = _fold(blk, dt, True)
+                t = F.conv2d(t, w, b, stride=blk.stride, padding=blk.conv.padding)
+                if blk.relu:
+                    t = F.relu_(t)
+            return t
+
+        conv0 = seq(self.conv0, x)
+        conv1 = seq(self.conv1, conv0)
+        conv2 = seq(self.conv2, conv1)
+        outputs = {"stage1": F.conv2d(conv2, _plain(self.out1, dt, True)[0])}
+        w, b = _plain(self.inner1, dt, True)
+        intra = F.interpolate(conv2, scale_factor=2, mode="nearest") + F.conv2d(conv1, w, b)
+        outputs["stage2"] = F.conv2d(intra, _plain(self.out2, dt, True)[0], padding=1)
+        w, b = _plain(self.inner2, dt, True)
+        intra = F.interpolate(intra, scale_factor=2, mode="nearest") + F.conv2d(conv0, w, b)
+        outputs["stage3"] = F.conv2d(intra, _plain(self.out3, dt, True)[0], padding=1)
+        return outputs
+
+    def forward(self, x, mode=None, emit_c8h=False):
+        """x [B,3,H,W] float (or uint8: normalised as float32(u8)/255 like the loader).  Returns the reference's dict
+        {"stage1": [B,32,H/4,W/4], "stage2": [B,16,H/2,W/2], "stage3": [B,8,H,W]}; with emit_c8h (fast mode only) the
+        maps come in the builder's C8H layout [B,C/8,h,w,8] fp16."""
+        mode = mode or self.mode
+        if x.dtype == torch.uint8:
+            x = x.float() / 255.0
+        if mode == "strict" or self.training:
+            if emit_c8h:
+                raise ValueError("emit_c8h needs mode='fast' (eval)")
+            return self._forward_strict(x.float())
+        out = self._forward_fast(x)
+        return {k: to_c8h(v) for k, v in out.items()} if emit_c8h else out
+
+
+class CascadeMVSNet(nn.Module):
+    """Drop-in for CasMVSNet/models/cas_mvsnet.py:69-165 (refine=False, share_cr supported): same constructor
+    arguments, same state-dict keys (feature.*, cost_regularization.N.*), same forward signature and output dict.
+    `mode`: "strict" (fp32 parity mode) or "fast" (fp16 extractor + C8H hand-off + tcgen05 CostRegNet)."""
+
+    def __init__(self, refine=False, ndepths=(48, 32, 8), depth_interals_ratio=(4, 2, 1), share_cr=False, grad_method="detach",
+                 arch_mode="fpn", cr_base_chs=(8, 8, 8), mode="strict"):
+        super().__init__()
+        if refine:
+            raise NotImplementedError("RefineNet is not on the hot path (the reference never enables it: train.py)")
+        assert len(ndepths) == len(depth_interals_ratio)
+        self.refine, self.share_cr, self.grad_method, self.arch_mode = refine, share_cr, grad_method, arch_mode
+        self.ndepths, self.depth_interals_ratio, self.cr_base_chs = list(ndepths), list(depth_interals_ratio), list(cr_base_chs)
+        self.num_stage, self.mode = len(ndepths), mode
+        self.feature = FeatureNet(base_channels=8, stride=4, num_stage=self.num_stage, arch_mode=arch_mode, mode=mode)
+        if share_cr:
+            raise NotImplementedError("share_cr=True needs equal stage channels, which the fpn extractor does not have")
+        self.cost_regularization = nn.ModuleList([
+            modules.CostRegNetCas(self.feature.out_channels[i], self.cr_base_chs[i], mode=mode) for i in range(self.num_stage)])
+        self.DepthNet = modules.DepthNet()
+
+    def extract(self, imgs: torch.Tensor) -> List[Dict[str, torch.Tensor]]:
+        """imgs [B,N,3,H,W] -> one feature dict per view.  fast: one batched extractor call over all B*N images
+        (view-major, so every view's maps are contiguous), C8H out; strict: the reference's loop (cas_mvsnet.py:115-118)."""
+        B, N = imgs.shape[:2]
+        if self.mode == "fast" and not self.training:
+            flat = imgs.transpose(0, 1).reshape(N * B, *imgs.shape[2:])
+            out = self.feature(flat, mode="fast", emit_c8h=True)
+            return [{k: t[v * B:(v + 1) * B] for k, t in out.items()} for v in range(N)]
+        return [self.feature(imgs[:, v], mode="strict") for v in range(N)]
+
+    def forward(self, imgs, proj_matrices, depth_values, depth_min=None, depth_max=None, stage_hook=None):
+        features = self.extract(imgs)
+        return cascade_hot_path(features, proj_matrices, depth_values, self.cost_regularization, ndepths=self.ndepths,
+                                depth_interals_ratio=self.depth_interals_ratio, img_hw=tuple(imgs.shape[-2:]),
+                                depth_min=depth_min, depth_max=depth_max, stage_hook=stage_hook)

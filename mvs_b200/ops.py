@@ -69,12 +69,17 @@ def _ptr_array(ts: Sequence[Optional[torch.Tensor]]):
     return arr
 
 
-def _depth_mode(depth: torch.Tensor, B: int):
+def _depth_mode(depth: torch.Tensor, B: int, hw=None):
+    """MVS_DEPTH_PLANE for [B,D], MVS_DEPTH_PIXEL for [B,D,H,W]; `hw` = the (H, W) extent the kernel will index the
+    per-pixel hypotheses with (a mismatch would be an out-of-bounds device read; the reference raises a shape error)."""
     if depth.dim() == 2:
         if depth.shape[0] != B:
             raise ValueError(f"depth_values batch {depth.shape[0]} != {B}")
         return L.DEPTH_PLANE
     if depth.dim() == 4:
+        if depth.shape[0] != B or (hw is not None and tuple(depth.shape[2:]) != tuple(hw)):
+            raise ValueError(f"per-pixel depth_values must be [{B},D,{hw[0] if hw else 'H'},{hw[1] if hw else 'W'}], "
+                             f"got {tuple(depth.shape)}")
         return L.DEPTH_PIXEL
     raise ValueError(f"depth_values must be [B,D] or [B,D,H,W], got {tuple(depth.shape)}")
 
@@ -95,9 +100,7 @@ def _warp(src_fea, rot, trans, depth_values, flags):
     _dev(src_fea, rot, trans, depth_values)
     B, Cc, H, W = src_fea.shape
     D = depth_values.shape[1]
-    mode = _depth_mode(depth_values, B)
-    if mode == L.DEPTH_PIXEL and tuple(depth_values.shape) != (B, D, H, W):
-        raise ValueError(f"per-pixel depth_values must be [B,D,{H},{W}], got {tuple(depth_values.shape)}")
+    mode = _depth_mode(depth_values, B, (H, W))
     out = torch.empty((B, Cc, D, H, W), dtype=torch.float32, device=src_fea.device)
     with torch.cuda.device(src_fea.device):
         check(lib().mvs_warp_fwd(_p(src_fea), _p(rot), _p(trans), _p(depth_values), mode, _p(out), B, Cc, D, H, W,
@@ -134,7 +137,7 @@ def warp_taps(rot, trans, depth_values, H, W, flags=0, want_ixy=True):
     depth_values = _f32c(depth_values)
     _dev(rot, trans, depth_values)
     B, D = depth_values.shape[0], depth_values.shape[1]
-    mode = _depth_mode(depth_values, B)
+    mode = _depth_mode(depth_values, B, (H, W))
     dev = depth_values.device
     x0 = torch.empty((B, D, H, W), dtype=torch.int32, device=dev)
     y0 = torch.empty_like(x0)
@@ -155,7 +158,7 @@ def _stack_pose(rots, transs):
 def _cost_volume_fwd(ref, srcs, rot, trans, depth_values, flags):
     B, Cc, H, W = ref.shape
     D = depth_values.shape[1]
-    mode = _depth_mode(depth_values, B)
+    mode = _depth_mode(depth_values, B, (H, W))
     nsrc = len(srcs)
     if nsrc < 1:
         raise ValueError("need at least one source view")
@@ -193,7 +196,7 @@ class _WarpFn(torch.autograd.Function):
         D = depth_values.shape[1]
         g_src = torch.zeros(ctx.shape, dtype=torch.float32, device=grad_out.device)
         with torch.cuda.device(grad_out.device):
-            check(lib().mvs_warp_bwd(_p(grad_out), _p(rot), _p(trans), _p(depth_values), _depth_mode(depth_values, B),
+            check(lib().mvs_warp_bwd(_p(grad_out), _p(rot), _p(trans), _p(depth_values), _depth_mode(depth_values, B, (H, W)),
                                      _p(g_src), B, Cc, D, H, W, ctx.flags, _stream()), "mvs_warp_bwd")
         return g_src, None, None, None, None
 
@@ -219,7 +222,7 @@ class _CostVolumeFn(torch.autograd.Function):
         g_srcs = [torch.zeros_like(s) for s in srcs]
         with torch.cuda.device(ref.device):
             check(lib().mvs_warp_variance_bwd(_p(grad_out), _p(ref), _ptr_array(srcs), len(srcs), _p(rot), _p(trans),
-                                              _p(depth_values), _depth_mode(depth_values, B), _p(g_ref),
+                                              _p(depth_values), _depth_mode(depth_values, B, (H, W)), _p(g_ref),
                                               _ptr_array(g_srcs), B, Cc, D, H, W, ctx.flags, _stream()),
                   "mvs_warp_variance_bwd")
         return (g_ref, None, None, None, None, *g_srcs)
@@ -263,9 +266,14 @@ FAST_FEATURE_DTYPE = torch.bfloat16 if __import__("os").environ.get("MVS_C8_FEAT
 
 
 def unpack_c8(x_c8: torch.Tensor, channels: int, dtype=torch.float32) -> torch.Tensor:
-    """C8 bf16 [B, CB, *spatial, 8] -> NC(D)HW `dtype`."""
+    """C8 bf16 [B, CB, *spatial, 8] -> NC(D)HW `dtype` (fp32 or bf16).  fp16 "C8H" feature maps are a one-way hand-off
+    format of the builder and cannot be unpacked."""
     _dev(x_c8)
-    assert x_c8.dtype == torch.bfloat16 and x_c8.shape[-1] == 8 and x_c8.is_contiguous()
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError(f"unpack_c8: dtype must be torch.float32 or torch.bfloat16, got {dtype}")
+    if x_c8.dtype != torch.bfloat16 or x_c8.shape[-1] != 8 or not x_c8.is_contiguous():
+        raise ValueError("unpack_c8: input must be a contiguous bf16 C8 tensor [B,CB,*spatial,8] "
+                         "(fp16 C8H feature maps are not supported)")
     B = x_c8.shape[0]
     spatial = tuple(x_c8.shape[2:-1])
     inner = 1
@@ -290,7 +298,7 @@ def cost_volume_c8(ref_c8, srcs_c8, rots, transs, depth_values, flags=0):
     _dev(ref_c8, rot, trans, depth_values, *srcs_c8)
     B, CB, H, W, _ = ref_c8.shape
     D = depth_values.shape[1]
-    mode = _depth_mode(depth_values, B)
+    mode = _depth_mode(depth_values, B, (H, W))
     nsrc = len(srcs_c8)
     if not 1 <= nsrc <= L.MAX_SRC:
         raise ValueError(f"1..{L.MAX_SRC} source views per fused call, got {nsrc}")
@@ -338,7 +346,7 @@ def softargmin_conf(logits, depth_values, clamp_index=False, want_prob=False, wa
     B, D, H, W = logits.shape
     if depth_values.dim() == 1:
         depth_values = depth_values.unsqueeze(0).expand(B, D).contiguous()
-    mode = _depth_mode(depth_values, B)
+    mode = _depth_mode(depth_values, B, (H, W))
     if depth_values.shape[1] != D:
         raise ValueError(f"depth_values has {depth_values.shape[1]} hypotheses, logits have {D}")
     dev = logits.device
@@ -353,16 +361,47 @@ def softargmin_conf(logits, depth_values, clamp_index=False, want_prob=False, wa
     return depth, conf, prob, index
 
 
-def depth_regression(p, depth_values):
-    """Drop-in for depth_regression(p, depth_values): MVSNet/models/module.py:91,
-    CasMVSNet/models/module.py:455 ([B,D] or [B,D,H,W]), CVP-MVSNet/models/modules.py:338.
-    `p` is a probability volume (already soft-maxed), as in the reference."""
+class _DepthRegressionFn(torch.autograd.Function):
+    """depth = sum_d p * depth_values with the reference's gradient structure (MVSNet/models/module.py:91-103 is plain
+    autograd): d depth / d p = depth_values, d depth / d depth_values = p.  The forward is the fused kernel."""
+
+    @staticmethod
+    def forward(ctx, p, depth_values):
+        ctx.save_for_backward(p, depth_values)
+        return softargmin_conf(p, depth_values, input_is_prob=True)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        p, dv = ctx.saved_tensors
+        g = g.unsqueeze(1)                                   # [B,1,H,W]
+        gp = gdv = None
+        if ctx.needs_input_grad[0]:
+            dvb = dv if dv.dim() == 4 else (dv.view(*dv.shape, 1, 1) if dv.dim() == 2 else dv.view(1, -1, 1, 1))
+            gp = (g * dvb).to(p.dtype)
+        if ctx.needs_input_grad[1]:
+            gd = g * p
+            gdv = gd if dv.dim() == 4 else (gd.sum((2, 3)) if dv.dim() == 2 else gd.sum((0, 2, 3)))
+            gdv = gdv.to(dv.dtype)
+        return gp, gdv
+
+
+def _regress_prob(p, depth_values):
+    if torch.is_grad_enabled() and (p.requires_grad or depth_values.requires_grad):
+        return _DepthRegressionFn.apply(p, depth_values)
     return softargmin_conf(p, depth_values, input_is_prob=True)[0]
 
 
+def depth_regression(p, depth_values):
+    """Drop-in for depth_regression(p, depth_values): MVSNet/models/module.py:91,
+    CasMVSNet/models/module.py:455 ([B,D] or [B,D,H,W]), CVP-MVSNet/models/modules.py:338, MVSNet_pl/models/modules.py:64.
+    `p` is a probability volume (already soft-maxed), as in the reference.  Differentiable w.r.t. `p` and
+    `depth_values` (the training path of MVSNet_pl/models/mvsnet.py:112 back-propagates through it)."""
+    return _regress_prob(p, depth_values)
+
+
 def depth_regression_refine(prob_volume, depth_hypothesis):
-    """Drop-in for CVP-MVSNet/models/modules.py:352."""
-    return softargmin_conf(prob_volume, depth_hypothesis, input_is_prob=True)[0]
+    """Drop-in for CVP-MVSNet/models/modules.py:352 (differentiable like depth_regression)."""
+    return _regress_prob(prob_volume, depth_hypothesis)
 
 
 def depth_range_samples(cur_depth, ndepth: int, depth_interval_pixel: float):

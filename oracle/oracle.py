@@ -90,8 +90,9 @@ def warp_taps(rot, trans, depth, H, W, flags=0):
     return x0, y0, mask, ixy
 
 
-def cost_volume(ref, srcs, rot, trans, depth, flags=0):
-    """ref [B,C,H,W], srcs [nsrc,B,C,H,W], rot [B,nsrc,3,3], trans [B,nsrc,3] -> var [B,C,D,H,W]."""
+def cost_volume(ref, srcs, rot, trans, depth, flags=0, rows=None):
+    """ref [B,C,H,W], srcs [nsrc,B,C,H,W], rot [B,nsrc,3,3], trans [B,nsrc,3] -> var [B,C,D,H,W]
+    (rows=(y0, y1): only reference rows y0..y1-1 -> [B,C,D,y1-y0,W]; full-size checks in seconds)."""
     ref, p_ref = _f(ref)
     srcs, p_srcs = _f(srcs)
     nsrc = srcs.shape[0]
@@ -100,9 +101,11 @@ def cost_volume(ref, srcs, rot, trans, depth, flags=0):
     depth, mode = _depth_mode(depth, B, D)
     rot, p_rot = _f(np.asarray(rot).reshape(B, nsrc, 9))
     trans, p_tr = _f(np.asarray(trans).reshape(B, nsrc, 3))
-    out = np.empty((B, Cc, D, H, W), np.float32)
-    lib().mvso_cost_volume(p_ref, p_srcs, nsrc, p_rot, p_tr, depth.ctypes.data_as(C.POINTER(C.c_float)),
-                           mode, out.ctypes.data_as(C.POINTER(C.c_float)), B, Cc, D, H, W, flags)
+    y0, y1 = rows if rows is not None else (0, H)
+    assert 0 <= y0 <= y1 <= H
+    out = np.empty((B, Cc, D, y1 - y0, W), np.float32)
+    lib().mvso_cost_volume_rows(p_ref, p_srcs, nsrc, p_rot, p_tr, depth.ctypes.data_as(C.POINTER(C.c_float)),
+                                mode, out.ctypes.data_as(C.POINTER(C.c_float)), B, Cc, D, H, W, flags, y0, y1)
     return out
 
 
@@ -180,6 +183,27 @@ def depth_range_samples(cur, interval, ndepth):
 # CostRegNet topologies composed from the C layer functions.  `sd` is a {key: ndarray} state dict
 # with the reference's own keys (SURVEY.md §5 "checkpoint / resume").
 # ------------------------------------------------------------------------------------------------
+def geo_pair(depth_ref, depth_src, cam, dist_thresh=1.0, rel_thresh=0.01):
+    """C restatement of reproject_with_depth + check_geometric_consistency (MVSNet/eval.py:138-208) with the float64
+    matmuls as explicit k-ordered FMA chains.  cam = the 60 float64 of mvs_b200.fusion.camera_block.
+    Returns dict(mask uint8, depth_reprojected, x_src, y_src, x_reprojected, y_reprojected) [H,W]."""
+    dr = np.ascontiguousarray(depth_ref, np.float32)
+    ds = np.ascontiguousarray(depth_src, np.float32)
+    cam = np.ascontiguousarray(cam, np.float64)
+    assert cam.shape == (60,) and dr.shape == ds.shape and dr.ndim == 2
+    H, W = dr.shape
+    names = ("depth_reprojected", "x_src", "y_src", "x_reprojected", "y_reprojected")
+    outs = {n: np.empty((H, W), np.float32) for n in names}
+    mask = np.empty((H, W), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn = lib().mvso_geo_pair
+    fn.restype = None
+    fn(vp(dr), vp(ds), vp(cam), vp(mask), *[vp(outs[n]) for n in names], C.c_int(H), C.c_int(W), C.c_double(dist_thresh),
+       C.c_float(rel_thresh))
+    outs["mask"] = mask
+    return outs
+
+
 def _cbr(x, sd, conv_key, bn_key, stride=1, transposed=False, skip=None, eps=1e-5):
     y = conv3d(x, sd[conv_key + ".weight"], None, stride, transposed)
     return bn_relu_skip(y, sd[bn_key + ".weight"], sd[bn_key + ".bias"], sd[bn_key + ".running_mean"],

@@ -499,3 +499,81 @@ def test_cas_hypotheses_fused_vs_composition(scale, nd):
     ref = F.interpolate(samples.unsqueeze(1), [nd, H // scale, W // scale], mode="trilinear", align_corners=False).squeeze(1)
     out = ops.cas_hypotheses(prev, (H, W), (H // scale, W // scale), nd, 2 * 2.65)
     np.testing.assert_allclose(npy(out), npy(ref), rtol=3e-7, atol=0)
+
+
+# ---- TMA-staged builder (warp_tma.cu) == L1-gather builder (warp_c8.cu), bit for bit ------------------------------
+def _c8h_case(n_views, B, C, H, W, D, seed, pixel, interval=10.6, baseline_gain=1.0):
+    v = cases.volume_case(n_views=n_views, B=B, C=C, H=H, W=W, D=D, seed=seed, per_pixel=pixel)
+    if pixel and interval != 10.6:
+        v["depth"] = cases.synth.depth_per_pixel(D, H, W, interval, B)
+    p = torch.from_numpy(v["proj"]).double()
+    prod = torch.stack([p[:, i] @ torch.inverse(p[:, 0]) for i in range(1, n_views)], 1)
+    prod[:, :, :3, 3] *= baseline_gain                       # wider baselines => larger per-depth motion => box overflow
+    rot, tr = rt(prod.float().numpy())
+    return v, rot, tr
+
+
+def _both_builders(feats, rot, tr, depth, flags=0):
+    from mvs_b200 import ops, _lib as L
+    nsrc = len(feats) - 1
+    rots = [cu(rot[:, i].reshape(-1, 9)) for i in range(nsrc)]
+    trs = [cu(tr[:, i]) for i in range(nsrc)]
+    packed = [ops.pack_c8(cu(f), torch.float16) for f in feats]
+    d = cu(depth)
+    tma = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, d, flags)
+    gather = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, d, flags | L.WARP_NO_TMA)
+    return tma, gather
+
+
+@pytest.mark.parametrize("C,pixel,nsrc,B,H,W,D", [
+    (32, False, 4, 1, 21, 40, 6), (16, True, 4, 2, 37, 50, 12), (8, True, 2, 1, 64, 96, 8), (8, False, 6, 1, 19, 33, 5),
+    (8, True, 1, 1, 8, 32, 3), (16, False, 8, 1, 24, 70, 9), (8, True, 4, 1, 2, 2, 2), (24, True, 3, 2, 130, 161, 17)])
+def test_tma_builder_equals_gather_builder(C, pixel, nsrc, B, H, W, D):
+    """Same taps, same weights, same op order: the staged box only decides WHERE a tap is read from."""
+    v, rot, tr = _c8h_case(nsrc + 1, B, C, H, W, D, 70 + C + nsrc, pixel)
+    tma, gather = _both_builders(v["feats"], rot, tr, v["depth"])
+    assert torch.equal(tma.view(torch.int16), gather.view(torch.int16))
+    assert not torch.isnan(tma.float()).any()
+
+
+@pytest.mark.parametrize("gain,interval,flags", [(6.0, 10.6, 0), (1.0, 400.0, 0), (25.0, 60.0, 0), (1.0, 10.6, 3), (1.0, 10.6, 4)])
+def test_tma_builder_box_overflow_and_flags(gain, interval, flags):
+    """Footprints far larger than the staged box (wide baselines, huge hypothesis spacing) take the per-lane global
+    fallback; align_corners + PL op order (3) and the CVP quirk (4) go through the same kernel.  Still bit-identical."""
+    v, rot, tr = _c8h_case(5, 1, 16, 72, 100, 16, 91, True, interval=interval, baseline_gain=gain)
+    tma, gather = _both_builders(v["feats"], rot, tr, v["depth"], flags)
+    assert torch.equal(tma.view(torch.int16), gather.view(torch.int16))
+
+
+def test_tma_builder_degenerate_inputs():
+    """Non-finite / negative / zero hypotheses and a singular pose: NaN voxels where the reference's CPU path has NaN,
+    identical bits to the gather kernel everywhere (NaN payloads included: both write the canonical 0x7fc0)."""
+    v, rot, tr = _c8h_case(3, 1, 8, 24, 40, 8, 93, True)
+    d = v["depth"].copy()
+    d[0, 1, 3:9, 5:17] = np.nan
+    d[0, 2, 10:14, :] = 0.0
+    d[0, 3, :, 20:30] = -300.0
+    d[0, 4, 0, 0] = np.inf
+    rot[0, 1] = 0.0
+    tma, gather = _both_builders(v["feats"], rot, tr, d)
+    assert torch.equal(tma.view(torch.int16), gather.view(torch.int16))
+    assert torch.isnan(tma.float()).any()
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_tma_builder_full_size_cfg3(stage):
+    """BASELINE cfg3 stage extents (N=5): TMA-staged == gather kernel bit for bit on the full volume, and a row band of
+    the result against the CPU oracle on the fp16-rounded features."""
+    C, D, H, W = cases.synth.CONFIGS["cfg3"]["stages"][stage]
+    v, rot, tr = _c8h_case(5, 1, C, H, W, D, 5 + stage, stage > 0, interval=(2.65 * (4, 2, 1)[stage]))
+    tma, gather = _both_builders(v["feats"], rot, tr, v["depth"])
+    assert torch.equal(tma.view(torch.int16), gather.view(torch.int16))
+    del gather
+    from mvs_b200 import ops
+    # CPU oracle on a band of reference rows (fp16-rounded features in, same tolerance as the small-size oracle tests)
+    y0, y1 = H // 2 - 3, H // 2 + 3
+    feats = torch.from_numpy(v["feats"]).half().float().numpy()
+    out = npy(ops.unpack_c8(tma, C))[:, :, :, y0:y1]
+    del tma
+    ref_band = O.cost_volume(feats[0], feats[1:], rot, tr, v["depth"], rows=(y0, y1))
+    np.testing.assert_allclose(out, ref_band, rtol=2 ** -7, atol=4e-3)
