@@ -1,21 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- depth-maps/sec of the MVSNet-family cost-volume hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode strict|fast]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode fast|strict]
+                    [--config cfg3|cfg5|cfg2]
 
-Workload (config.workload): BASELINE.json configs[2] = "cfg3": CasMVSNet 3-stage hot path at DTU
-1600x1184, N=5 views, D=(48,32,8) -- the configuration the metric is quoted on; it fits one GPU.
-One step = one reference view through warp+variance -> CostRegNet -> softmax/regression/confidence
-for all three stages (incl. the inter-stage hypothesis resampling), from feature maps to the final
-depth + confidence maps.  Synthetic DTU-shaped inputs (mvs_b200/synth.py), seeded weights.
+Default workload (config.workload): BASELINE.json configs[2] = "cfg3": CasMVSNet 3-stage, DTU 1600x1184, N=5 views,
+D=(48,32,8) -- the configuration the metric is quoted on; it fits one GPU.  `--config cfg5` (Tanks&Temples shape
+1920x1056, N=7, D=64/32/8, 4 reference views per GPU per step) and `--config cfg2` (MVSNet 640x512, N=5, D=192, batch 4)
+run BASELINE.json configs[4] / [1] through the same code.
 
-N > 1: one process per GPU (torchrun), every rank runs its own reference views (the path shards over
-independent reference views; inference has no collective) => weak scaling; the only communication
-is the barrier and the max-over-ranks of the device time.
+What is timed (one "step" = one batch of reference views through the path):
+  value        hot path only, inputs resident in HBM in the hand-off format the repo's FeatureNet mirror emits (fp16 C8H
+               feature maps): warp+variance -> CostRegNet -> softmax/regression/confidence for every stage incl. the
+               inter-stage hypothesis resampling.  CUDA-graph replay; `eager_ms_per_step` = launch by launch, the pass
+               the per-kernel CUDA events of `roofline` come from.
+  from_images  the whole model (FeatureNet mirror + hot path) from device-resident uint8 images.
+  e2e          what the reference's driver does per sample (CasMVSNet/test.py:176-181: tocuda -> model(imgs, proj_matrices,
+               depth_values) -> tensor2numpy): uint8 images in PINNED HOST memory -> H2D -> whole model -> D2H of depth +
+               confidence, copies inside the timed region and overlapped with the neighbouring steps on side streams.
+  strict       the same hot path in strict fp32 mode (the 1e-4 parity mode), so that "speed at which parity" is a
+               driver-run number.
+  parity       measured in-run on this workload at full size against the reference's op sequence executed on the same GPU in
+               fp32 with TF32 off (oracle/torch_port.py: checker, outside every timed region).
+N > 1: one process per GPU (torchrun), every rank runs its own reference views (independent units, no data-path
+collective at inference) => weak scaling; the only communication is the barrier and the max-over-ranks of the device time.
 
-`--impl reference`: the reference's own CPU implementation of the path (its PyTorch op sequence,
-restated in oracle/torch_port.py because /root/reference cannot travel to the GPU box), with all
-host threads, on a bounded row-crop of the same workload per step.
+`--impl reference`: the reference's own CPU implementation of the path from images (its PyTorch op sequence incl. the
+FeatureNet, restated in oracle/torch_port.py because /root/reference cannot travel to the GPU box), all host threads,
+one FULL reference view per step.
 """
 from __future__ import annotations
 
@@ -40,39 +52,64 @@ import torch
 
 from mvs_b200 import synth
 
-METRIC = "depth-maps/sec (ref-views/sec) at DTU 1600x1184, N=5"
 UNIT = "depth-maps/s"
-CFG = synth.CONFIGS["cfg3"]
-NDEPTHS = (48, 32, 8)
-IMG_HW = (1184, 1600)
-CPU_SAMPLE_ROWS = 320          # full-res rows per CPU-baseline step (of 1184): keeps every stage /8-divisible
+WORKLOADS = {
+    "cfg3": dict(kind="cas", key="cfg3", img_hw=(1184, 1600), ndepths=(48, 32, 8),
+                 metric="depth-maps/sec (ref-views/sec) at DTU 1600x1184, N=5",
+                 name="cfg3: CasMVSNet 3-stage 1600x1184 N=5 D=(48,32,8), 1 ref view per GPU per step"),
+    "cfg5": dict(kind="cas", key="cfg5", img_hw=(1056, 1920), ndepths=(64, 32, 8),
+                 metric="depth-maps/sec (ref-views/sec) at Tanks&Temples 1920x1056, N=7",
+                 name="cfg5: CasMVSNet 3-stage 1920x1056 N=7 D=(64,32,8), 4 ref views per GPU per step"),
+    "cfg2": dict(kind="mvsnet", key="cfg2", img_hw=(512, 640), ndepths=(192,),
+                 metric="depth-maps/sec (ref-views/sec) at 640x512, N=5, D=192",
+                 name="cfg2: MVSNet 640x512 N=5 D=192, 4 ref views per GPU per step"),
+}
+SEED_MODEL = 40
 
 
-# ------------------------------------------------------------------------------------------------
-def host_inputs(seed=0, rows=IMG_HW[0]):
-    """Feature maps (per view, per stage), Cas projection matrices, depth values -- NumPy, fp32."""
-    n = CFG["n_views"]
-    feats, projs = [dict() for _ in range(n)], {}
-    for i, (c, d, h, w) in enumerate(CFG["stages"]):
-        key = f"stage{i + 1}"
-        hh = h * rows // IMG_HW[0]
-        f = synth.features(n, c, hh, w, seed + i, 1)
-        for v in range(n):
-            feats[v][key] = f[v]
-        projs[key] = synth.cas_proj_matrices(n, w, seed, 1)
-    return feats, projs, synth.depth_planes(192, 1)
+# ------------------------------------------------------------------------------------------------------------------
+def host_inputs(wl, seed=0, batch=None):
+    """uint8 images [B,N,3,H,W], projection matrices, depth values -- NumPy, as the loader hands them."""
+    cfg = synth.CONFIGS[wl["key"]]
+    n, B = cfg["n_views"], batch or cfg["batch"]
+    H, W = wl["img_hw"]
+    if wl["kind"] == "cas":
+        projs = {f"stage{i + 1}": synth.cas_proj_matrices(n, W // s, seed, B) for i, s in enumerate((4, 2, 1))}
+        return dict(imgs=synth.images_u8(n, H, W, seed, B), projs=projs, depth_values=synth.depth_planes(192, B))
+    c, d, h, w = cfg["stages"][0]
+    return dict(feats=synth.features(n, c, h, w, seed, B), projs=synth.proj_matrices(n, w, seed, B),
+                depth_values=synth.depth_planes(d, B, hi=synth.DTU_DEPTH_MIN + 2.65 * d))
 
 
-def weights():
+def model_state(wl):
     import cases
-    return [cases.costreg_state("cas", cin=c, base=8, seed=50 + i) for i, (c, _, _, _) in enumerate(CFG["stages"])]
+    if wl["kind"] == "cas":
+        return cases.full_model_state(SEED_MODEL)
+    return cases.costreg_state("mvsnet", seed=SEED_MODEL)
 
 
-def algorithmic_bytes(mode):
+def algorithmic_bytes(wl, mode, batch):
+    cfg = synth.CONFIGS[wl["key"]]
     s = 4 if mode == "strict" else 2
-    per_stage = [synth.warp_variance_bytes(CFG["n_views"], 1, c, d, h, w, s, s, per_pixel_depth=(i > 0))
-                 for i, (c, d, h, w) in enumerate(CFG["stages"])]
-    return per_stage
+    return [synth.warp_variance_bytes(cfg["n_views"], batch, c, d, h, w, s, s, per_pixel_depth=(wl["kind"] == "cas" and i > 0))
+            for i, (c, d, h, w) in enumerate(cfg["stages"])]
+
+
+def pin_to_gpu_numa(index):
+    """Bind this process to the CPUs next to its GPU before any pinned allocation (first touch places the pinned pages on
+    that NUMA node); eight ranks streaming from one node was the 8-GPU e2e limiter of round 1.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -117,53 +154,66 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------
-def run_cpu_port(steps, warmup, rows):
-    """The reference's op sequence on the host cores (oracle/torch_port.py), row-cropped sample."""
+# ------------------------------------------------------------------------------------------------------------------
+# checker / baseline legs (oracle/torch_port.py; never inside a timed region of the repo arm)
+def _port_inputs(wl, dev, batch=None):
+    hi = host_inputs(wl, batch=batch)
+    sd = {k: torch.from_numpy(np.asarray(a)).to(dev) for k, a in model_state(wl).items()}
+    dv = torch.from_numpy(hi["depth_values"]).to(dev)
+    if wl["kind"] == "cas":
+        imgs = torch.from_numpy(hi["imgs"]).to(dev).float() / 255.0          # general_eval.py:81-86
+        projs = {k: torch.from_numpy(a).to(dev) for k, a in hi["projs"].items()}
+        return dict(imgs=imgs, projs=projs, dv=dv, sd=sd)
+    feats = [torch.from_numpy(f).to(dev) for f in hi["feats"]]
+    return dict(feats=feats, projs=torch.from_numpy(hi["projs"]).to(dev), dv=dv, sd=sd)
+
+
+def _port_step(wl, pi, features=None):
     from oracle import torch_port as TP
+    if wl["kind"] == "cas":
+        if features is not None:
+            sds = [{k[len(f"cost_regularization.{i}."):]: v for k, v in pi["sd"].items() if k.startswith(f"cost_regularization.{i}.")}
+                   for i in range(len(wl["ndepths"]))]
+            return TP.cas_cascade(features, pi["projs"], pi["dv"], sds, ndepths=wl["ndepths"], img_hw=wl["img_hw"])
+        return TP.cas_model(pi["imgs"], pi["projs"], pi["dv"], pi["sd"], ndepths=wl["ndepths"])
+    projs = torch.unbind(pi["projs"], 1)
+    var = TP.variance_volume(pi["feats"][0], pi["feats"][1:], projs[0], projs[1:], pi["dv"])
+    depth, conf = TP.regress(TP.costreg(var, pi["sd"], "mvsnet"), pi["dv"], clamp_index=False)
+    return {"depth": depth, "photometric_confidence": conf}
+
+
+def run_cpu_port(wl, steps, warmup):
+    """The reference's op sequence on the host cores, ONE full reference view per step (batch 1 of the config's batch)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    feats, projs, dv = host_inputs(rows=rows)
-    tf = [{k: torch.from_numpy(a) for k, a in f.items()} for f in feats]
-    tp = {k: torch.from_numpy(a) for k, a in projs.items()}
-    sds = [{k: torch.from_numpy(np.asarray(a)) for k, a in sd.items()} for sd in weights()]
-    tdv = torch.from_numpy(dv)
+    pi = _port_inputs(wl, "cpu", batch=1)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            TP.cas_cascade(tf, tp, tdv, sds, ndepths=NDEPTHS, img_hw=(rows, IMG_HW[1]))
+            _port_step(wl, pi)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    frac = rows / IMG_HW[0]
     total = sum(times)
-    return {"value": frac * len(times) / total, "ms_per_step": 1e3 * total / len(times), "frac": frac,
-            "cores": torch.get_num_threads(),
-            "sample": f"rows 0..{rows - 1} of {IMG_HW[0]} ({100 * frac:.0f}% of one cfg3 ref view: all 3 stages, full "
-                      f"width/D/C/N) per step, {len(times)} step(s), torch {torch.__version__} CPU, fp32"}
+    what = "images -> FeatureNet x N views -> 3-stage cascade" if wl["kind"] == "cas" else "feature maps -> cost volume -> CostRegNet -> regression"
+    return {"value": len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": torch.get_num_threads(),
+            "sample": f"1 full reference view per step ({what}; full H/W/D/C/N of {wl['key']}), {len(times)} step(s), "
+                      f"torch {torch.__version__} CPU, fp32, oracle/torch_port.py"}
 
 
-def run_gpu_port(dev, steps, warmup, autocast):
-    """SURVEY.md §8(d) "reference GPU baseline beside it": the reference's op sequence
-    (oracle/torch_port.py = grid_sample + cuDNN conv3d + BN/ReLU + softmax, its stock code path) on
-    the same B200, full cfg3 ref view, cudnn.benchmark=True as the reference's train.py:25 sets it.
-    A reported baseline (checker code timed as the thing to beat), never on the product path."""
-    from oracle import torch_port as TP
-    feats, projs, dv = host_inputs()
-    tf = [{k: torch.from_numpy(a).to(dev) for k, a in f.items()} for f in feats]
-    tp = {k: torch.from_numpy(a).to(dev) for k, a in projs.items()}
-    sds = [{k: torch.from_numpy(np.asarray(a)).to(dev) for k, a in sd.items()} for sd in weights()]
-    tdv = torch.from_numpy(dv).to(dev)
+def run_gpu_port(wl, dev, steps, warmup):
+    """SURVEY.md 8(d) "reference GPU baseline beside it": the reference's op sequence (grid_sample + cuDNN conv3d + BN/ReLU +
+    softmax, incl. its FeatureNet) on the same B200, cudnn.benchmark=True as the reference's train.py:25 sets it.  A reported
+    baseline (checker code timed as the thing to beat), never on the product path."""
+    pi = _port_inputs(wl, dev, batch=1)
     old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.benchmark = True
     torch.backends.cudnn.allow_tf32 = True
     out = {}
     try:
         for name, ac in (("fp32_tf32", False), ("autocast_bf16", True)):
-            if ac and not autocast:
-                continue
             def one():
                 with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
-                    return TP.cas_cascade(tf, tp, tdv, sds, ndepths=NDEPTHS, img_hw=IMG_HW)
+                    return _port_step(wl, pi)
             for _ in range(warmup):
                 one()
             torch.cuda.synchronize()
@@ -177,37 +227,52 @@ def run_gpu_port(dev, steps, warmup, autocast):
             out[name] = {"value": 1e3 / ms, "ms_per_step": ms}
     finally:
         torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-    del tf, sds
+    del pi
     torch.cuda.empty_cache()
     return out
 
 
-def main_reference(args):
+def depth_errors(ours, ref, keys):
+    """Per stage: relative L-inf and relative L1 of the depth map, fraction of pixels within 1e-4 / 1e-3 relative."""
+    out = {}
+    for k in keys:
+        a, b = ours[k]["depth"].double(), ref[k]["depth"].double()
+        rel = (a - b).abs() / b.abs()
+        out[k] = {"depth_rel_linf": float(rel.max()), "depth_rel_l1": float((a - b).abs().mean() / b.abs().mean()),
+                  "frac_within_1e-4": float((rel <= 1e-4).double().mean()), "frac_within_1e-3": float((rel <= 1e-3).double().mean())}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = run_cpu_port(args.steps, args.warmup, CPU_SAMPLE_ROWS)
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+    r = run_cpu_port(wl, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": wl["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3: CasMVSNet 3-stage hot path 1600x1184 N=5 D=(48,32,8)",
-                       "sample_fraction_per_step": r["frac"]},
+            "config": {"workload": wl["name"], "sample_fraction_per_step": 1.0,
+                       "inputs": "uint8 images scaled by 1/255 (the loader's read_img), full view"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------
-def main_ours(args):
+# ------------------------------------------------------------------------------------------------------------------
+def main_ours(args, wl):
     import torch.distributed as dist
     from mvs_b200 import modules, cascade, ops, _lib
+    from mvs_b200.featurenet import CascadeMVSNet
+    from mvs_b200.graph import GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; mvs_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    numa_cpus = pin_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -217,29 +282,6 @@ def main_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    feats_np, projs_np, dv_np = host_inputs(seed=rank)
-    regs = []
-    for (c, _, _, _), sd in zip(CFG["stages"], weights()):
-        net = modules.CostRegNet(c, 8, mode=args.mode)
-        net.load_state_dict({k: torch.from_numpy(np.asarray(a)) for k, a in sd.items()}, strict=True)
-        regs.append(net.to(dev).eval())
-    # hand-off dtype of the 2D FeatureNet: bf16 in fast mode (cfg3 is "bf16 inference": what the reference's
-    # autocast FeatureNet emits), fp32 in strict mode.  NCHW either way; packed to C8 inside the step.
-    fdt = torch.bfloat16 if args.mode == "fast" else torch.float32
-    pinned = [{k: torch.from_numpy(a).to(fdt).pin_memory() for k, a in f.items()} for f in feats_np]
-    feats = [{k: t.to(dev) for k, t in f.items()} for f in pinned]
-    projs = {k: torch.from_numpy(a).to(dev) for k, a in projs_np.items()}
-    dv = torch.from_numpy(dv_np).to(dev)
-    dmin, dmax = float(dv_np[0, 0]), float(dv_np[0, -1])
-    h2d_bytes = sum(t.numel() * t.element_size() for f in pinned for t in f.values())
-    host_out = [torch.empty(1, *IMG_HW, dtype=torch.float32).pin_memory() for _ in range(2)]
-    d2h_bytes = sum(t.numel() * 4 for t in host_out)
-
-    def step(fs):
-        with torch.no_grad():
-            return cascade.cascade_hot_path(fs, projs, dv, regs, ndepths=NDEPTHS, img_hw=IMG_HW, depth_min=dmin,
-                                            depth_max=dmax)
 
     def timed(fn, k, tail=None):
         barrier()
@@ -256,108 +298,154 @@ def main_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    cfg = synth.CONFIGS[wl["key"]]
+    B, cas = cfg["batch"], wl["kind"] == "cas"
+    hi = host_inputs(wl, seed=rank)
+    sd = {k: torch.from_numpy(np.asarray(a)) for k, a in model_state(wl).items()}
+    dv = torch.from_numpy(hi["depth_values"]).to(dev)
+    dmin, dmax = float(hi["depth_values"][0, 0]), float(hi["depth_values"][0, -1])
+    keys = [f"stage{i + 1}" for i in range(len(wl["ndepths"]))] if cas else None
+
+    def build_model(mode):
+        if cas:
+            m = CascadeMVSNet(ndepths=wl["ndepths"], mode=mode)
+            m.load_state_dict(sd, strict=True)
+        else:
+            m = modules.CostRegNet(mode=mode)
+            m.load_state_dict(sd, strict=True)
+        return m.to(dev).eval()
+
+    model = build_model(args.mode)
+    if cas:
+        projs = {k: torch.from_numpy(a).to(dev) for k, a in hi["projs"].items()}
+        host_in = [torch.from_numpy(hi["imgs"]).pin_memory()]                                   # uint8 [B,N,3,H,W]
+        imgs_dev = host_in[0].to(dev)
+        with torch.no_grad():
+            feats = model.extract(imgs_dev)             # hand-off format of the mode: C8H fp16 (fast) / NCHW fp32 (strict)
+
+        def hot_step(fs=feats, m=model):
+            with torch.no_grad():
+                return cascade.cascade_hot_path(fs, projs, dv, m.cost_regularization, ndepths=wl["ndepths"], img_hw=wl["img_hw"],
+                                                depth_min=dmin, depth_max=dmax)
+
+        def full_step(im, m=model):
+            with torch.no_grad():
+                return m(im, projs, dv, depth_min=dmin, depth_max=dmax)
+        out_shape = (B, *wl["img_hw"])
+    else:
+        projs = torch.from_numpy(hi["projs"]).to(dev)
+        fdt = torch.float16 if args.mode == "fast" else torch.float32
+        fl = [torch.from_numpy(f).to(dev) for f in hi["feats"]]
+        feats = [ops.pack_c8(f, torch.float16) for f in fl] if args.mode == "fast" else fl
+        host_in = [f.cpu().pin_memory() for f in feats]                                          # hand-off: feature maps
+        del fl
+
+        def hot_step(fs=feats, m=model):
+            with torch.no_grad():
+                return modules.mvsnet_hot_path(list(fs), projs, dv, m)
+        full_step = None
+        out_shape = (B, *cfg["stages"][0][2:])
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_in)
+    d2h_bytes = 2 * int(np.prod(out_shape)) * 4
+
     # ---- pass 1 (eager launches, per-kernel CUDA events): roofline of the fused builder + the eager step time ----
     for _ in range(max(args.warmup, 3)):
-        step(feats)
+        hot_step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = _lib.launch_count()
     ops.KERNEL_TIMERS = {}
-    ms_eager = timed(lambda: step(feats), args.steps)
+    ms_eager = timed(hot_step, args.steps)
     timers, ops.KERNEL_TIMERS = ops.KERNEL_TIMERS, None
     launches_per_step = (_lib.launch_count() - n0) // args.steps
 
-    # ---- pass 2 (the deployment form): the same step captured once in a CUDA graph (mvs_b200.GraphedStep) and
-    # replayed -- ~85 launches per ref view cost more host time than GPU time once issued one by one from Python ----
+    # ---- pass 2 (the deployment form): the same step captured once in a CUDA graph and replayed ----
     use_graph = not args.no_graph
     if use_graph:
-        from mvs_b200.graph import GraphedStep
-        g_res = GraphedStep(lambda: step(feats))
+        g_hot = GraphedStep(hot_step)
         for _ in range(2):
-            g_res()
-        ms = timed(g_res, args.steps)
+            g_hot()
+        ms = timed(g_hot, args.steps)
     else:
         ms = ms_eager
     clocks = sampler.stop() if rank == 0 else None
-    launches = launches_per_step * args.steps
 
-    # ---- e2e: every step copies ITS inputs from pinned host memory and reads its result back.  The copy of
-    # step i+1 runs on a copy stream into the other half of a double buffer while step i computes, stage by stage
-    # (coarse stage first; the compute stream waits per STAGE through cascade_hot_path's stage_hook, so stage 1 starts
-    # after 14 % of the bytes have landed); the read-back of step i-1 runs on its own stream (PCIe is full duplex).
-    # Nothing is reused across steps.  Two launch forms are measured, the better one is reported:
-    #   "graph"  whole step replayed from a CUDA graph after ALL of its inputs have landed,
-    #   "staged" eager launches with the per-stage waits.
-    copy_stream = torch.cuda.Stream(device=dev)
-    d2h_stream = torch.cuda.Stream(device=dev)
-    NBUF = 3            # device-side input buffers: the copy of step i+1 only waits for the compute of step i-2
-    dbuf = [[{k: torch.empty_like(t, device=dev) for k, t in f.items()} for f in pinned] for _ in range(NBUF)]
-    stage_keys = [f"stage{i + 1}" for i in range(len(NDEPTHS))]
-    ev_stage = [[torch.cuda.Event() for _ in stage_keys] for _ in range(NBUF)]
+    # ---- whole model from device-resident images (FeatureNet mirror + hot path) ----
+    from_images = None
+    NBUF = 2
+    if cas:
+        dbuf = [torch.empty_like(host_in[0], device=dev) for _ in range(NBUF)]
+        for t in dbuf:
+            t.copy_(host_in[0])
+        g_full = [GraphedStep(lambda j=j: full_step(dbuf[j])) for j in range(NBUF)] if use_graph else None
+        run_full = (lambda j: g_full[j]()) if use_graph else (lambda j: full_step(dbuf[j]))
+        ms_full = timed(lambda: run_full(0), args.steps)
+        from_images = {"value": world * B * args.steps / (ms_full * 1e-3), "unit": UNIT, "ms_per_step": ms_full / args.steps,
+                       "what": "FeatureNet mirror (fp16 channels-last PyTorch/cuDNN, all N views batched, C8H out) + hot path, "
+                               "uint8 images resident in HBM"}
+    else:
+        dbuf = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(NBUF)]
+        g_full = [GraphedStep(lambda j=j: hot_step(dbuf[j])) for j in range(NBUF)] if use_graph else None
+        run_full = (lambda j: g_full[j]()) if use_graph else (lambda j: hot_step(dbuf[j]))
+
+    # ---- e2e: every step copies ITS inputs from pinned host memory and reads its result back; the copy of step i+1 (copy
+    # stream) and the read-back of step i-1 (its own stream; PCIe is full duplex) overlap the compute of step i ----
+    copy_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    ev_in = [torch.cuda.Event() for _ in range(NBUF)]
     ev_free = [torch.cuda.Event() for _ in range(NBUF)]
     ev_d2h = [torch.cuda.Event() for _ in range(NBUF)]
-    host_outs = [[torch.empty(1, *IMG_HW, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(NBUF)]
-    g_e2e = [GraphedStep(lambda j=j: step(dbuf[j])) for j in range(NBUF)] if use_graph else None
+    host_outs = [[torch.empty(out_shape, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(NBUF)]
+    counter = [0]
 
-    def make_step_e2e(form):
-        counter = [0]
-
-        def step_e2e():
-            i = counter[0]; counter[0] += 1
-            j = i % NBUF
-            cur = torch.cuda.current_stream()
-            with torch.cuda.stream(copy_stream):
-                if i >= NBUF:
-                    copy_stream.wait_event(ev_free[j])       # the step that last read this buffer has finished
-                for si, key in enumerate(stage_keys):
-                    for fd, fh in zip(dbuf[j], pinned):
-                        fd[key].copy_(fh[key], non_blocking=True)
-                    ev_stage[j][si].record(copy_stream)
+    def step_e2e():
+        i = counter[0]; counter[0] += 1
+        j = i % NBUF
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
             if i >= NBUF:
-                cur.wait_event(ev_d2h[j])                    # the read-back of this half's previous result has finished
-            if form == "graph":
-                cur.wait_event(ev_stage[j][-1])
-                out = g_e2e[j]()
+                copy_stream.wait_event(ev_free[j])           # the step that last read this input buffer has finished
+            if cas:
+                dbuf[j].copy_(host_in[0], non_blocking=True)
             else:
-                with torch.no_grad():
-                    out = cascade.cascade_hot_path(dbuf[j], projs, dv, regs, ndepths=NDEPTHS, img_hw=IMG_HW, depth_min=dmin,
-                                                   depth_max=dmax, stage_hook=lambda si: cur.wait_event(ev_stage[j][si]))
-            ev_free[j].record(cur)
-            with torch.cuda.stream(d2h_stream):
-                d2h_stream.wait_event(ev_free[j])
-                host_outs[j][0].copy_(out["depth"], non_blocking=True)
-                host_outs[j][1].copy_(out["photometric_confidence"], non_blocking=True)
-                ev_d2h[j].record(d2h_stream)
-        return step_e2e
+                for d, h in zip(dbuf[j], host_in):
+                    d.copy_(h, non_blocking=True)
+            ev_in[j].record(copy_stream)
+        cur.wait_event(ev_in[j])
+        if i >= NBUF:
+            cur.wait_event(ev_d2h[j])                        # this buffer's previous result has left the device
+        out = run_full(j)
+        ev_free[j].record(cur)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ev_free[j])
+            host_outs[j][0].copy_(out["depth"], non_blocking=True)
+            host_outs[j][1].copy_(out["photometric_confidence"], non_blocking=True)
+            out["depth"].record_stream(d2h_stream); out["photometric_confidence"].record_stream(d2h_stream)
+            ev_d2h[j].record(d2h_stream)
 
-    def e2e_tail():                                      # the timed region ends when the LAST result has landed on the host
+    def e2e_tail():                                          # the timed region ends when the LAST result has landed on the host
         cur = torch.cuda.current_stream()
         for j in range(NBUF):
             cur.wait_event(ev_d2h[j])
 
-    e2e_forms = {}
-    for form in (["graph"] if use_graph else []) + ["staged"]:
-        fn = make_step_e2e(form)
-        for _ in range(NBUF):
-            fn()
-        e2e_forms[form] = timed(fn, args.steps, e2e_tail)
-    e2e_form = min(e2e_forms, key=e2e_forms.get)
-    ms_e2e = e2e_forms[e2e_form]
+    for _ in range(NBUF + 1):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps, e2e_tail)
 
-    # the same host->device copies alone (no compute): shows how much of the e2e step is the PCIe transfer
     def h2d_only():
-        for fd, fh in zip(dbuf[0], pinned):
-            for k, t in fh.items():
-                fd[k].copy_(t, non_blocking=True)
+        if cas:
+            dbuf[0].copy_(host_in[0], non_blocking=True)
+        else:
+            for d, h in zip(dbuf[0], host_in):
+                d.copy_(h, non_blocking=True)
     h2d_only()
     ms_h2d = timed(h2d_only, args.steps)
 
-    # roofline of the fused warp+variance kernel from the events recorded inside the timed region
+    # ---- roofline of the fused warp+variance kernel from the events recorded inside the timed eager pass ----
     ev = timers.get("warp_variance", [])
     kernel_ms = sum(a.elapsed_time(b) for a, b in ev)
     n_launch = len(ev)
-    per_stage = algorithmic_bytes(args.mode)
+    per_stage = algorithmic_bytes(wl, args.mode, B)
     alg_bytes = sum(per_stage) * (n_launch / len(per_stage))
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -365,56 +453,146 @@ def main_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    stage_ms = [sum(a.elapsed_time(b) for a, b in ev[i::len(per_stage)]) / max(len(ev[i::len(per_stage)]), 1) for i in range(len(per_stage))]
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = run_cpu_port(1, 0, CPU_SAMPLE_ROWS) if (world == 1 and not args.no_cpu_baseline) else None
+
+    # ---- single-GPU extras (rank 0, N = 1): strict mode, in-run parity, CPU and cuDNN baselines ----
+    extras = {}
+    if world == 1 and not args.no_parity:
+        try:
+            extras.update(parity_and_strict(args, wl, dev, model, build_model, hi, projs, dv, dmin, dmax, keys))
+        except Exception as e:   # reported side numbers must never take the bench line down
+            extras["parity"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    cpu = run_cpu_port(wl, 1, 0) if (world == 1 and not args.no_cpu_baseline) else None
     ref_gpu = None
     if world == 1 and not args.no_ref_gpu:
         try:
-            ref_gpu = run_gpu_port(dev, 5, 3, True)
-        except Exception as e:   # a reported side number must never take the bench line down
+            ref_gpu = run_gpu_port(wl, dev, 5, 3)
+        except Exception as e:
             ref_gpu = {"error": f"{type(e).__name__}: {e}"[:200]}
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "warp_variance_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.mode)
+    if os.path.exists(tpath) and wl["key"] == "cfg3":
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get(args.mode), "static: " + tj.get("source", "ncu capture committed under profiles/")
     line = {
-        "metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": wl["metric"], "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "strict" else "bf16",
         "data": "synthetic", "eager_ms_per_step": ms_eager / args.steps,
         "launch": ("CUDA graph replay of the captured step (mvs_b200.GraphedStep); eager_ms_per_step = the same step issued "
                    "launch by launch from Python, the pass the per-kernel events of `roofline` come from") if use_graph
                   else "eager launches",
-        "config": {"workload": "cfg3: CasMVSNet 3-stage hot path 1600x1184 N=5 D=(48,32,8), 1 ref view per GPU per step",
-                   "mode": args.mode, "l2": "inputs+intermediates per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                   "features": ("bf16" if args.mode == "fast" else "fp32") + " NCHW feature maps (packed to fp16 C8H inside the step in fast mode)"},
-        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+        "config": {"workload": wl["name"], "mode": args.mode, "ref_views_per_step": B,
+                   "l2": "inputs+intermediates per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                   "features": "value: feature maps resident in HBM in the hand-off format of the FeatureNet mirror "
+                               + ("(fp16 C8H)" if args.mode == "fast" else "(fp32 NCHW)"),
+                   "numa_cpus": numa_cpus},
+        "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
-                "h2d_only_ms_per_step": ms_h2d / args.steps, "form": e2e_form,
-                "ms_per_step_by_form": {k: v / args.steps for k, v in e2e_forms.items()},
-                "note": "input copy (per stage, coarse first) overlaps compute on a copy stream, read-back on a third stream; "
-                        "the step is PCIe-bound when h2d_only_ms_per_step ~ ms_per_step"},
-        "gpu_launches": int(launches),
-        "roofline": {"kernel": "warp_variance (fused homography warp + variance, 3 launches/step)", "bound": "hbm",
+                "h2d_only_ms_per_step": ms_h2d / args.steps,
+                "what": ("pinned uint8 images [B,N,3,H,W] -> H2D -> /255 + FeatureNet mirror + hot path -> D2H depth + confidence "
+                         "(the reference's model(imgs, proj_matrices, depth_values) boundary)") if cas else
+                        "pinned fp16 C8H feature maps -> H2D -> hot path -> D2H depth + confidence (no MVSNet FeatureNet mirror yet)",
+                "note": "input copy of step i+1 and read-back of step i-1 overlap step i on side streams"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": {"kernel": f"warp_variance (fused homography warp + variance, {len(per_stage)} launch(es)/step)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
+                     "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                      "avg_launch_ms": kernel_ms / max(n_launch, 1), "launches_timed": n_launch,
+                     "per_stage_ms": stage_ms, "per_stage_frac": [b / (t * 1e-3) / 1e9 / peak if t > 0 else None for b, t in zip(per_stage, stage_ms)],
                      "share_of_step": kernel_ms / ms_eager if ms_eager > 0 else None},
         "clocks": clocks,
     }
+    if from_images is not None:
+        line["from_images"] = from_images
+    line.update(extras)
     if cpu is not None:
-        line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
-                                "sample": cpu["sample"]}
+        line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
     if ref_gpu is not None:
-        line["ref_gpu_baseline"] = {"unit": UNIT, "what": "reference op sequence (grid_sample + cuDNN conv3d, oracle/torch_port.py) "
-                                    "on the same GPU, full cfg3 ref view, cudnn.benchmark=True, features resident", **ref_gpu}
+        line["ref_gpu_baseline"] = {"unit": UNIT, "what": "reference op sequence (FeatureNet + grid_sample + cuDNN conv3d, oracle/torch_port.py) "
+                                    "on the same GPU from images, 1 ref view per step, cudnn.benchmark=True", **ref_gpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_and_strict(args, wl, dev, model, build_model, hi, projs, dv, dmin, dmax, keys):
+    """In-run parity at the benchmarked size (checker = the reference's op sequence on the same GPU, fp32, TF32 off) and the
+    strict-mode step time.  Not timed as part of `value`."""
+    from mvs_b200 import modules, cascade, ops
+    from oracle import torch_port as TP
+    out = {}
+    cas = wl["kind"] == "cas"
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    try:
+        pi = _port_inputs(wl, dev)
+        with torch.no_grad():
+            if cas:
+                feats32 = [TP.featurenet(pi["imgs"][:, v], pi["sd"], "feature.") for v in range(pi["imgs"].shape[1])]
+                ref_hot = _port_step(wl, pi, features=feats32)
+                ks = keys
+            else:
+                feats32 = pi["feats"]
+                r = _port_step(wl, pi)
+                ref_hot = {"stage1": r}
+                ks = ["stage1"]
+        strict = model if args.mode == "strict" else build_model("strict")
+        fast = model if args.mode == "fast" else build_model("fast")
+
+        def hot(m, fs):
+            with torch.no_grad():
+                if cas:
+                    return cascade.cascade_hot_path(fs, projs, dv, m.cost_regularization, ndepths=wl["ndepths"], img_hw=wl["img_hw"],
+                                                    depth_min=dmin, depth_max=dmax)
+                return {"stage1": modules.mvsnet_hot_path(list(fs), projs, dv, m)}
+
+        res = {}
+        for name, m in (("strict", strict), ("fast", fast)):
+            res[name] = depth_errors(hot(m, feats32), ref_hot, ks)
+        last = ks[-1]
+        cur = res[args.mode][last]
+        out["parity"] = {"mode": args.mode, "depth_rel_linf": cur["depth_rel_linf"], "depth_l1": cur["depth_rel_l1"],
+                         "vs": "reference op sequence (oracle/torch_port.py) on the same GPU, fp32, TF32 off, same fp32 feature maps in; "
+                               "final-stage depth at the benchmarked size; errors compound through the cascade",
+                         "hot_path": res}
+        if cas:
+            with torch.no_grad():
+                imgs_u8 = torch.from_numpy(hi["imgs"]).to(dev)
+                ref_full = _port_step(wl, pi)
+                full = {name: depth_errors(m(imgs_u8, projs, dv, depth_min=dmin, depth_max=dmax), ref_full, ks)
+                        for name, m in (("strict", strict), ("fast", fast))}
+            out["parity"]["from_images"] = full
+        # strict-mode step time (hot path, features resident): the "speed at 1e-4" number
+        if args.mode == "fast" and not args.no_strict:
+            with torch.no_grad():
+                fs = strict.extract(torch.from_numpy(hi["imgs"]).to(dev)) if cas else feats32
+            for _ in range(2):
+                hot(strict, fs)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            n = 3
+            for _ in range(n):
+                hot(strict, fs)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n
+            B = synth.CONFIGS[wl["key"]]["batch"]
+            out["strict"] = {"ms_per_step": ms, "value": B * 1e3 / ms, "unit": UNIT, "dtype": "f32",
+                             "parity": res["strict"][last], "what": "same hot path, strict fp32 kernels (parity mode), eager launches"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":
@@ -424,11 +602,15 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fast", choices=["strict", "fast"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (no CUDA graph replay)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-cuDNN side measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check and the strict-mode timing")
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode timing")
     a = ap.parse_args()
+    w = WORKLOADS[a.config]
     if a.impl == "reference":
-        main_reference(a)
+        main_reference(a, w)
     else:
-        main_ours(a)
+        main_ours(a, w)

@@ -44,7 +44,8 @@ extern "C" {
 #define MVS_BLEND_BF16 64       /* C8 builder: bilinear blend in packed bf16x2 (sums / variance stay fp32) */
 #define MVS_FAST_COORDS 128     /* mvs_warp_taps: probe the C8 builder's division-free-call tap arithmetic */
 #define MVS_FEAT_F16 256        /* C8 builder: feature maps are fp16 C8 (mvs_pack_c8h); blend in packed fp16  */
-#define MVS_WARP_NO_TMA 512     /* C8 builder: force the L1-gather kernel (default for fp16 maps: TMA-staged boxes) */
+#define MVS_WARP_NO_TMA 512     /* C8 builder: force the L1-gather kernel                                       */
+#define MVS_WARP_TMA 1024       /* C8 builder: force the TMA-staged kernel (fp16 maps only); neither bit: library picks */
 
 /* depth_mode */
 #define MVS_DEPTH_PLANE 0       /* depth [B,D]       MVSNet/models/module.py:46                   */

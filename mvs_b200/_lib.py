@@ -22,6 +22,7 @@ BLEND_BF16 = 64
 FAST_COORDS = 128
 FEAT_F16 = 256
 WARP_NO_TMA = 512
+WARP_TMA = 1024
 DEPTH_PLANE = 0
 DEPTH_PIXEL = 1
 F32 = 0

@@ -119,6 +119,22 @@ def features(n_views: int, c: int, h: int, w: int, seed: int = 0, batch: int = 1
     return rng.standard_normal((n_views, batch, c, h, w)).astype(np.float32)
 
 
+def images_u8(n_views: int, h: int, w: int, seed: int = 0, batch: int = 1) -> np.ndarray:
+    """[B,n_views,3,h,w] uint8 images: smooth structure + noise, as a decoded JPEG would hand them to the loader
+    (CasMVSNet/datasets/general_eval.py:81-86 then scales by 1/255)."""
+    rng = np.random.RandomState(4000 + seed)
+    y, x = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    out = np.empty((batch, n_views, 3, h, w), np.uint8)
+    for b in range(batch):
+        for v in range(n_views):
+            for c in range(3):
+                ph = rng.uniform(0, 2 * math.pi, 2)
+                f = rng.uniform(0.02, 0.2, 2)
+                img = 127.5 + 70.0 * np.sin(f[0] * x + ph[0]) * np.cos(f[1] * y + ph[1]) + 25.0 * rng.standard_normal((h, w))
+                out[b, v, c] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return out
+
+
 def fill_state_dict(shapes: dict, seed: int = 0) -> dict:
     """Deterministic weights for a CostRegNet ``state_dict`` given ``{key: shape}``.
 
@@ -140,6 +156,9 @@ def fill_state_dict(shapes: dict, seed: int = 0) -> dict:
         elif len(shp) == 5:
             fan = shp[1] * 27
             a = 1.0 / math.sqrt(fan)
+            out[key] = rng.uniform(-a, a, shp).astype(np.float32)
+        elif len(shp) == 4:        # 2D convolution of the feature extractor: Kaiming-uniform scale keeps activations O(1)
+            a = math.sqrt(6.0 / (shp[1] * shp[2] * shp[3]))
             out[key] = rng.uniform(-a, a, shp).astype(np.float32)
         elif key.endswith("weight"):
             out[key] = rng.uniform(0.5, 1.5, shp).astype(np.float32)

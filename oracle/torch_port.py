@@ -158,3 +158,36 @@ def cas_cascade(features, proj_matrices, depth_values, sds, ndepths=(48, 32, 8),
         out[key] = {"depth": d, "photometric_confidence": c}
     out.update(out[f"stage{len(ndepths)}"])
     return out
+
+
+# ---- the caller side: CasMVSNet's FPN extractor and the whole model from images ----------------
+def _c2d(x, sd, name, stride=1, pad=1, eps=1e-5):
+    """Conv2d block = conv (no bias) + BatchNorm2d (eval) + ReLU: CasMVSNet/models/module.py:26-66."""
+    y = F.conv2d(x, sd[name + ".conv.weight"], None, stride=stride, padding=pad)
+    y = F.batch_norm(y, sd[name + ".bn.running_mean"], sd[name + ".bn.running_var"], sd[name + ".bn.weight"],
+                     sd[name + ".bn.bias"], False, 0.1, eps)
+    return F.relu(y, inplace=True)
+
+
+def featurenet(x, sd, prefix=""):
+    """FeatureNet.forward, arch_mode="fpn", num_stage=3: CasMVSNet/models/module.py:366-405.  x [B,3,H,W]."""
+    p = prefix
+    conv0 = _c2d(_c2d(x, sd, p + "conv0.0"), sd, p + "conv0.1")
+    conv1 = _c2d(_c2d(_c2d(conv0, sd, p + "conv1.0", 2, 2), sd, p + "conv1.1"), sd, p + "conv1.2")
+    conv2 = _c2d(_c2d(_c2d(conv1, sd, p + "conv2.0", 2, 2), sd, p + "conv2.1"), sd, p + "conv2.2")
+    intra = conv2
+    out = {"stage1": F.conv2d(intra, sd[p + "out1.weight"])}
+    intra = F.interpolate(intra, scale_factor=2, mode="nearest") + F.conv2d(conv1, sd[p + "inner1.weight"], sd[p + "inner1.bias"])
+    out["stage2"] = F.conv2d(intra, sd[p + "out2.weight"], padding=1)
+    intra = F.interpolate(intra, scale_factor=2, mode="nearest") + F.conv2d(conv0, sd[p + "inner2.weight"], sd[p + "inner2.bias"])
+    out["stage3"] = F.conv2d(intra, sd[p + "out3.weight"], padding=1)
+    return out
+
+
+def cas_model(imgs, proj_matrices, depth_values, sd, ndepths=(48, 32, 8), ratios=(4, 2, 1)):
+    """CascadeMVSNet.forward from images (cas_mvsnet.py:109-165): per-view extractor loop (:115-118) + the cascade.
+    imgs [B,N,3,H,W] float32; sd = the whole model's state dict (feature.*, cost_regularization.N.*)."""
+    features = [featurenet(imgs[:, v], sd, "feature.") for v in range(imgs.shape[1])]
+    sds = [{k[len(f"cost_regularization.{i}."):]: v for k, v in sd.items() if k.startswith(f"cost_regularization.{i}.")}
+           for i in range(len(ndepths))]
+    return cas_cascade(features, proj_matrices, depth_values, sds, ndepths=ndepths, ratios=ratios, img_hw=tuple(imgs.shape[-2:]))

@@ -68,6 +68,47 @@ def costreg_state(family: str, cin: int = 32, base: int = 8, seed: int = 0) -> d
     return synth.fill_state_dict(costreg_shapes(family, cin, base), seed)
 
 
+# ---- CasMVSNet FeatureNet (fpn, base 8): state-dict shapes of CasMVSNet/models/module.py:304-365 ----
+def featurenet_shapes(base: int = 8) -> dict:
+    s = {}
+
+    def blk(name, cin, cout, k):
+        s[name + ".conv.weight"] = (cout, cin, k, k)
+        for t, shp in (("weight", (cout,)), ("bias", (cout,)), ("running_mean", (cout,)), ("running_var", (cout,)),
+                       ("num_batches_tracked", ())):
+            s[f"{name}.bn.{t}"] = shp
+
+    b = base
+    blk("conv0.0", 3, b, 3); blk("conv0.1", b, b, 3)
+    blk("conv1.0", b, 2 * b, 5); blk("conv1.1", 2 * b, 2 * b, 3); blk("conv1.2", 2 * b, 2 * b, 3)
+    blk("conv2.0", 2 * b, 4 * b, 5); blk("conv2.1", 4 * b, 4 * b, 3); blk("conv2.2", 4 * b, 4 * b, 3)
+    s["out1.weight"] = (4 * b, 4 * b, 1, 1)
+    s["inner1.weight"] = (4 * b, 2 * b, 1, 1); s["inner1.bias"] = (4 * b,)
+    s["inner2.weight"] = (4 * b, b, 1, 1); s["inner2.bias"] = (4 * b,)
+    s["out2.weight"] = (2 * b, 4 * b, 3, 3)
+    s["out3.weight"] = (b, 4 * b, 3, 3)
+    return s
+
+
+def featurenet_state(seed: int = 0) -> dict:
+    return synth.fill_state_dict(featurenet_shapes(), seed)
+
+
+def full_model_case(n_views=3, B=1, H=64, W=96, ndepths=(16, 8, 8), seed=9):
+    """Whole CascadeMVSNet from uint8 images (the loader's /255 scaling applied by the caller / on the device)."""
+    projs = {f"stage{i + 1}": synth.cas_proj_matrices(n_views, W // s, seed, B) for i, s in enumerate((4, 2, 1))}
+    return dict(imgs_u8=synth.images_u8(n_views, H, W, seed, B), projs=projs, depth_values=synth.depth_planes(192, B),
+                ndepths=list(ndepths), H=H, W=W)
+
+
+def full_model_state(seed: int = 40) -> dict:
+    """state_dict of the whole CascadeMVSNet: feature.* + cost_regularization.{0,1,2}.*"""
+    sd = {"feature." + k: v for k, v in featurenet_state(seed).items()}
+    for i, cin in enumerate((32, 16, 8)):
+        sd.update({f"cost_regularization.{i}." + k: v for k, v in costreg_state("cas", cin=cin, base=8, seed=seed + 1 + i).items()})
+    return sd
+
+
 # ---- warp / cost-volume cases -------------------------------------------------------------------
 def warp_plane_case(B=2, C=4, H=24, W=32, D=5, seed=1):
     fea = synth.features(2, C, H, W, seed, B)

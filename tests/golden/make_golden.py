@@ -272,7 +272,34 @@ def gen_pl():
     save("pl_homo_warp", out=out.numpy(), proj=(t(c["src_proj"]) @ ref_inv).numpy())
 
 
-GEN = {"mvsnet": gen_mvsnet, "cas": gen_cas, "cvp": gen_cvp, "pl": gen_pl}
+def gen_casfeat():
+    """The caller side: the reference's own FeatureNet (CasMVSNet/models/module.py:304-405) and the
+    WHOLE CascadeMVSNet.forward from images (cas_mvsnet.py:109-165), nothing stubbed."""
+    import torch
+    import cases
+    sys.path.insert(0, os.path.join(REF, "CasMVSNet"))
+    from models.module import FeatureNet
+    from models.cas_mvsnet import CascadeMVSNet
+
+    torch.set_grad_enabled(False)
+    fn = FeatureNet(base_channels=8, stride=4, num_stage=3, arch_mode="fpn").eval()
+    load_sd(fn, cases.featurenet_state(33))
+    img = t(cases.synth.images_u8(2, 48, 80, seed=21)[0]).float() / 255.0          # general_eval.py:81-86
+    out = fn(img)
+    save("cas_featurenet", **{k: v.numpy() for k, v in out.items()})
+
+    k = cases.full_model_case()
+    model = CascadeMVSNet(ndepths=k["ndepths"]).eval()
+    load_sd(model, cases.full_model_state())
+    res = model(t(k["imgs_u8"]).float() / 255.0, {s: t(p) for s, p in k["projs"].items()}, t(k["depth_values"]))
+    arrays = {}
+    for s in ("stage1", "stage2", "stage3"):
+        arrays[s + "_depth"] = res[s]["depth"].numpy()
+        arrays[s + "_conf"] = res[s]["photometric_confidence"].numpy()
+    save("cas_full_model", **arrays)
+
+
+GEN = {"mvsnet": gen_mvsnet, "cas": gen_cas, "cvp": gen_cvp, "pl": gen_pl, "casfeat": gen_casfeat}
 
 if __name__ == "__main__":
     if not os.path.isdir(REF):

@@ -520,7 +520,7 @@ def _both_builders(feats, rot, tr, depth, flags=0):
     trs = [cu(tr[:, i]) for i in range(nsrc)]
     packed = [ops.pack_c8(cu(f), torch.float16) for f in feats]
     d = cu(depth)
-    tma = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, d, flags)
+    tma = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, d, flags | L.WARP_TMA)
     gather = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, d, flags | L.WARP_NO_TMA)
     return tma, gather
 

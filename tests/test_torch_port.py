@@ -55,3 +55,33 @@ def test_costreg_state_dict_keys_match_reference_shapes():
         want = cases.costreg_shapes(fam, 16, 8)
         have = {k: tuple(v.shape) for k, v in net.state_dict().items()}
         assert have == {k: tuple(s) for k, s in want.items()}, fam
+
+
+def test_featurenet_port_and_mirror_match_reference():
+    """The reference's own FeatureNet output (tests/golden/cas_featurenet.npz) vs (a) the torch port the CPU arm times
+    and (b) the repo's state-dict-compatible mirror in strict mode (both the same ATen op sequence: bit-exact)."""
+    from mvs_b200.featurenet import FeatureNet
+    gold = cases.golden("cas_featurenet")
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in cases.featurenet_state(33).items()}
+    img = torch.from_numpy(cases.synth.images_u8(2, 48, 80, seed=21)[0])
+    with torch.no_grad():
+        port = TP.featurenet(img.float() / 255.0, sd)
+        net = FeatureNet(mode="strict").eval()
+        net.load_state_dict(sd, strict=True)                     # the reference's exact key set
+        mirror = net(img)                                        # uint8 in: normalised like the loader
+    for k in ("stage1", "stage2", "stage3"):
+        assert np.array_equal(port[k].numpy(), gold[k]), k
+        assert np.array_equal(mirror[k].numpy(), gold[k]), k
+
+
+def test_full_model_port_matches_reference():
+    """CascadeMVSNet.forward from images, nothing stubbed (tests/golden/cas_full_model.npz)."""
+    gold = cases.golden("cas_full_model")
+    k = cases.full_model_case()
+    sd = {n: torch.from_numpy(np.asarray(v)) for n, v in cases.full_model_state().items()}
+    with torch.no_grad():
+        out = TP.cas_model(torch.from_numpy(k["imgs_u8"]).float() / 255.0, {s: torch.from_numpy(p) for s, p in k["projs"].items()},
+                           torch.from_numpy(k["depth_values"]), sd, ndepths=k["ndepths"])
+    for s in ("stage1", "stage2", "stage3"):
+        np.testing.assert_allclose(out[s]["depth"].numpy(), gold[s + "_depth"], rtol=1e-6)
+        np.testing.assert_allclose(out[s]["photometric_confidence"].numpy(), gold[s + "_conf"], rtol=1e-5, atol=1e-6)

@@ -56,7 +56,7 @@ def main():
         for mode in modes:
             if mode in ("c8", "c8b", "c8h", "c8g"):     # c8h: fp16 maps, TMA-staged kernel; c8g: fp16 maps, L1-gather kernel
                 packed = [ops.pack_c8(f, torch.float16 if mode in ("c8h", "c8g") else torch.bfloat16) for f in feats]
-                fl = 64 if mode == "c8b" else (512 if mode == "c8g" else 0)        # MVS_BLEND_BF16 / MVS_WARP_NO_TMA
+                fl = 64 if mode == "c8b" else (512 if mode == "c8g" else (1024 if mode == "c8h" else 0))        # MVS_BLEND_BF16 / MVS_WARP_NO_TMA
                 fn = lambda: ops.cost_volume_c8(packed[0], packed[1:], rots, trs, depth, fl)
                 s = 2
             else:
