@@ -45,6 +45,7 @@ extern "C" {
 #define MVS_FAST_COORDS 128     /* mvs_warp_taps: probe the C8 builder's division-free-call tap arithmetic */
 #define MVS_FEAT_F16 256        /* C8 builder: feature maps are fp16 C8 (mvs_pack_c8h); blend in packed fp16  */
 #define MVS_WARP_NO_TMA 512     /* C8 builder: force the L1-gather kernel                                       */
+#define MVS_ACT_F16 2048        /* conv3d_c8: activations, packed weights and output are fp16 C8 instead of bf16 C8   */
 #define MVS_WARP_TMA 1024       /* C8 builder: force the TMA-staged kernel (fp16 maps only); neither bit: library picks */
 
 /* depth_mode */
@@ -55,6 +56,7 @@ extern "C" {
 #define MVS_F32 0
 #define MVS_BF16 1
 #define MVS_F16 2
+#define MVS_U8 3
 
 #define MVS_MAX_SRC 8           /* source views the fused builder takes in one launch            */
 
@@ -121,6 +123,20 @@ int mvs_unpack_c8(const void *src_c8, void *dst, int dst_dtype, int B, int C, in
  * clamped to +-65504 (fp16 max) instead of overflowing to infinity. */
 int mvs_pack_c8h(const void *src, int src_dtype, void *dst_c8h, int B, int C, int64_t inner, void *stream);
 
+/* ---- f3 (next row): the FeatureNet hand-off around the 3x3 convolutions (CasMVSNet/models/module.py:304-405) --------
+ * The 2D FPN extractor's 3x3 layers run on mvs_conv3d_c8_fwd with D = 1 and MVS_ACT_F16; these three kernels are the rest:
+ *   mvs_img_to_c8h     images [N,3,H,W] (MVS_F32, or MVS_U8 scaled by 1/255 like CasMVSNet/datasets/general_eval.py:81-86)
+ *                      -> fp16 C8 [N,1,H,W,8], channels 3..7 zero
+ *   mvs_s2d_c8         2x2 space-to-depth [N,CB,H,W,8] -> [N,4*CB,ceil(H/2),ceil(W/2),8], block order (py*2+px)*CB + cb:
+ *                      turns the 5x5 stride-2 pad-2 layers (module.py:336,342) into 3x3 stride-1 layers over 4*Cin channels
+ *   mvs_fpn_merge_c8h  out = nearest_up2(prev) + conv1x1(x) + bias (module.py:393-398): x [N,Cin/8,H,W,8], Cin in {8,16};
+ *                      w_host [32,Cin] / bias_host [32] are HOST pointers (copied into the kernel parameter block);
+ *                      prev [N,4,Hp,Wp,8] or NULL; out [N,4,H,W,8]; all maps fp16 C8. */
+int mvs_img_to_c8h(const void *img, int src_dtype, void *dst_c8h, int N, int H, int W, void *stream);
+int mvs_s2d_c8(const void *src_c8, void *dst_c8, int N, int CB, int H, int W, void *stream);
+int mvs_fpn_merge_c8h(const void *x_c8h, const float *w_host, const float *bias_host, const void *prev_c8h,
+                      void *out_c8h, int N, int Cin, int H, int W, int Hp, int Wp, void *stream);
+
 /* ---- a3: 3x3x3 convolution + folded BatchNorm + ReLU + skip ------------------------------------
  * Replaces ConvBnReLU3D / Conv3d / Deconv3d blocks and the skip adds of CostRegNet.forward:
  *   MVSNet/models/module.py:26-33, mvsnet.py:55-93; CasMVSNet/models/module.py:115-200,407-438;
@@ -142,6 +158,10 @@ int mvs_conv3d_fwd(const float *x, const float *w, const float *scale, const flo
 int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stride, int transposed);
 int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride,
                                int transposed, void *stream);
+/* flags: MVS_ACT_F16 packs fp16 blocks for mvs_conv3d_c8_fwd(..., flags | MVS_ACT_F16) -- the 2D feature extractor
+ * (CasMVSNet/models/module.py:304-405) runs on this kernel with D = 1 and fp16 C8 activations. */
+int mvs_conv3d_c8_pack_weights_ex(const float *w, void *packed, int Cin, int Cout, int stride,
+                                  int transposed, int flags, void *stream);
 int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const float *scale, const float *shift,
                       const void *skip_c8, void *y, int B, int Cin, int Cout, int D, int H, int W,
                       int stride, int transposed, int flags, void *stream);

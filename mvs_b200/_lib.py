@@ -23,10 +23,13 @@ FAST_COORDS = 128
 FEAT_F16 = 256
 WARP_NO_TMA = 512
 WARP_TMA = 1024
+ACT_F16 = 2048
 DEPTH_PLANE = 0
 DEPTH_PIXEL = 1
 F32 = 0
 BF16 = 1
+F16 = 2
+U8 = 3
 MAX_SRC = 8
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -46,9 +49,13 @@ SIGNATURES = {
     "mvs_pack_c8": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
     "mvs_unpack_c8": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp]),
     "mvs_pack_c8h": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
+    "mvs_img_to_c8h": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    "mvs_s2d_c8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "mvs_fpn_merge_c8h": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "mvs_conv3d_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
     "mvs_conv3d_c8_packed_weight_bytes": (_i64, [_i] * 4),
     "mvs_conv3d_c8_pack_weights": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
+    "mvs_conv3d_c8_pack_weights_ex": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
     "mvs_conv3d_c8_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
     "mvs_conv3d_c8_set_trace": (_i, [_vp, _i]),
     "mvs_softargmin_conf_fwd": (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i] * 5 + [_vp]),

@@ -101,6 +101,7 @@ struct ConvPlan {
     int od_mul, oh_mul, w_mul;
     int n_ops, n_acc, steps;
     int relu, out_f32, has_skip;
+    int f16;                  // MVS_ACT_F16: activations / weights / output are fp16 instead of bf16 (same 16-bit C8 layout)
     int n_issuers, zero_units;                      // zero_units: 16 B units of the all-zero B block (merged mode)
     int merged;                                     // stride-1 kh-merged mode: 2 issuers alternate depth steps, epilogue frees slabs
     // T-merged mode (stride 1): ONE MMA per (input row, k-step) carries all nine (row tap, step tap) weights along N,
@@ -130,6 +131,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48)
 // | base_offset[49,52)=0 | lbo_mode[52]=0 | layout_type[61,64)=0 (SWIZZLE_NONE / interleave); all in 16 B
 // units.  The issue loop assembles it as (kDescHi << 32) | (start + LBO << 16).
+
+// fp16 operands: a_format = b_format = 0
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n)
+{
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n)
 {
@@ -261,6 +268,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b)
+{
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2 *>(&u)); }
 
 // ---- the kernel -----------------------------------------------------------------------------------
 // MC = CTAs per SM the register allocator must allow (old modes): 3 for layers that live on occupancy, 2 for the
@@ -434,10 +447,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         v = __ffma2_rn(v, scl[e], shl[e]);
                         if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
                         if (kSkip) {
-                            v.x += __uint_as_float(sv[e] << 16);
-                            v.y += __uint_as_float(sv[e] & 0xffff0000u);
+                            if (P.f16) { const float2 s2 = unpack_f16x2(sv[e]); v.x += s2.x; v.y += s2.y; }
+                            else { v.x += __uint_as_float(sv[e] << 16); v.y += __uint_as_float(sv[e] & 0xffff0000u); }
                         }
-                        pk[e] = pack_bf16x2(v.x, v.y);
+                        pk[e] = P.f16 ? pack_f16x2(v.x, v.y) : pack_bf16x2(v.x, v.y);
                     }
                     ybase[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 };
@@ -624,7 +637,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 uint32_t leader;
                 asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
                 const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
-                const uint32_t idesc0 = umma_idesc_bf16(128, 0);
+                const uint32_t idesc0 = P.f16 ? umma_idesc_f16(128, 0) : umma_idesc_bf16(128, 0);
                 constexpr uint32_t kDescHi = 8u | (1u << 14);
                 RoleTimer rt; rt.start(trace && lane == 0 && iss == 0, trace, 3);
                 int slot = iss, q = 0;                     // sl = q * ring + slot (ring is even and >= 2, so slot = iss < ring)
@@ -677,7 +690,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             uint32_t leader;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
             const uint32_t sa_units = smem_u32(sa) >> 4, sw_units = smem_u32(sw) >> 4;
-            const uint32_t idesc0 = umma_idesc_bf16(128, 0);        // N comes from the op entry
+            const uint32_t idesc0 = P.f16 ? umma_idesc_f16(128, 0) : umma_idesc_bf16(128, 0);        // N comes from the op entry
             constexpr uint32_t kDescHi = 8u | (1u << 14);           // SBO = 8 units (128 B) | version = 1 (bit 46)
             // merged mode: the issuers alternate depth steps (issuer j owns TMEM buffer j and the whole op
             // table); otherwise every issuer works on every step with its own slice of accumulators
@@ -791,10 +804,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), scl[e], shl[e]);
                     if (P.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); }
                     if (kSkip) {
-                        t.x += __uint_as_float(sv[e] << 16);
-                        t.y += __uint_as_float(sv[e] & 0xffff0000u);
+                        if (P.f16) { const float2 s2 = unpack_f16x2(sv[e]); t.x += s2.x; t.y += s2.y; }
+                        else { t.x += __uint_as_float(sv[e] << 16); t.y += __uint_as_float(sv[e] & 0xffff0000u); }
                     }
-                    pk[e] = pack_bf16x2(t.x, t.y);
+                    pk[e] = P.f16 ? pack_f16x2(t.x, t.y) : pack_bf16x2(t.x, t.y);
                 }
                 ybase[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             };
@@ -898,7 +911,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 // Packs fp32 weights into the per-k-step B blocks: [cout_tile][kstep][2 chunks][nblk][N rows][8] bf16
 // (nblk = 3 for kh-merged stride-1 layers: blocks ordered kh = 2, 1, 0; else 1).
 __global__ void __launch_bounds__(256)
-pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, __nv_bfloat16 *__restrict__ out)
+pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, uint16_t *__restrict__ out, int f16)
 {
     const int rows_pc = P.nblk * P.n + P.pad_rows;               // rows per K chunk of a B block
     const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * rows_pc * 8;
@@ -906,7 +919,7 @@ pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict_
         long long t = i;
         const int e = (int)(t % 8); t /= 8;
         const int rr = (int)(t % rows_pc); t /= rows_pc;
-        if (rr >= P.nblk * P.n) { out[i] = __float2bfloat16_rn(0.f); continue; }
+        if (rr >= P.nblk * P.n) { out[i] = 0; continue; }
         const int row = rr % P.n, blk = rr / P.n;
         const int j = (int)(t % 2); t /= 2;
         const int ks = (int)(t % P.n_ksteps);
@@ -919,7 +932,7 @@ pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict_
             const int tt = P.flip ? 26 - tap : tap;
             v = P.transposed_weights ? w[((size_t)ci * P.cout + co) * 27 + tt] : w[((size_t)co * P.cin + ci) * 27 + tt];
         }
-        out[i] = __float2bfloat16_rn(v);
+        out[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
     }
 }
 
@@ -1089,7 +1102,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         P.Do = D; P.Ho = H; P.Wo = W;
         P.cin_chunks = g.cin_chunks; P.cout = Cout; P.cout_chunks = (Cout + 7) / 8; P.n = g.n; P.cout_tiles = g.cout_tiles;
         P.mode = g.mode; P.arr = 1; P.tmerged = 1;
-        P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip;
+        P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip; P.f16 = (flags & MVS_ACT_F16) ? 1 : 0;
         P.rd = 3; P.d_mul = 1;
         const int rows_pc = 9 * g.n + g.pad_rows, n3 = 3 * g.n;
         const int packed_units = (int)g.ks.size() * 2 * rows_pc;
@@ -1155,7 +1168,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
     else { P.Do = D; P.Ho = H; P.Wo = W; }
     P.cin_chunks = g.cin_chunks; P.cout = Cout; P.cout_chunks = (Cout + 7) / 8; P.n = g.n; P.cout_tiles = g.cout_tiles;
     P.mode = g.mode; P.arr = g.arr;
-    P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip;
+    P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip; P.f16 = (flags & MVS_ACT_F16) ? 1 : 0;
     const int S = g.mode == UM_CONV_S2 ? 2 : 1;
     const int acc_per_row = deconv ? 8 : 1;
     const int packed_units = (int)g.ks.size() * 2 * g.nblk * g.n;     // what mvs_conv3d_c8_pack_weights wrote per Cout tile
@@ -1323,6 +1336,12 @@ extern "C" int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stri
 extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride, int transposed,
                                           void *stream)
 {
+    return mvs_conv3d_c8_pack_weights_ex(w, packed, Cin, Cout, stride, transposed, 0, stream);
+}
+
+extern "C" int mvs_conv3d_c8_pack_weights_ex(const float *w, void *packed, int Cin, int Cout, int stride, int transposed,
+                                             int flags, void *stream)
+{
     MVS_REQUIRE(w && packed, "null pointer");
     MVS_REQUIRE(Cin > 0 && Cout > 0 && (stride == 1 || stride == 2), "bad layer shape");
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
@@ -1336,7 +1355,7 @@ extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin,
     pp.pad_rows = g.pad_rows;
     const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * (g.nblk * g.n + g.pad_rows) * 8;
     pack_weights_kernel<<<cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        pp, w, (__nv_bfloat16 *)packed);
+        pp, w, (uint16_t *)packed, (flags & MVS_ACT_F16) ? 1 : 0);
     return check_launch("mvs_conv3d_c8_pack_weights");
 }
 

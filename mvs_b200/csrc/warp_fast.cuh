@@ -38,7 +38,8 @@ __device__ __forceinline__ float div_by_rcp(float a, float b, float r)
 
 // Sample position (ix, iy) of ref pixel (x, y) at `depth` in the source image: the reference's exact op
 // sequence (warp_common.cuh contract), shared by the builder and the tap probe.
-template <bool PL>
+// AC: -1 = align_corners read from g at run time, 0 / 1 = compile-time
+template <bool PL, int AC = -1>
 __device__ __forceinline__ void tap_position(const float q[3], const float rt[12], const GeomC8 &g, float x, float y,
                                              float depth, float &ix, float &iy)
 {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void tap_position(const float q[3], const float rt[12
     const float u = div_by_rcp(P0, P2, r), v = div_by_rcp(P1, P2, r);
     const float gx = __fsub_rn(div_by_rcp(u, g.half_wm1, g.r_hw), 1.0f);
     const float gy = __fsub_rn(div_by_rcp(v, g.half_hm1, g.r_hh), 1.0f);
-    if (g.align_corners) {
+    if (AC < 0 ? (g.align_corners != 0) : (AC != 0)) {
         ix = __fmul_rn(__fadd_rn(gx, 1.0f), g.sx);
         iy = __fmul_rn(__fadd_rn(gy, 1.0f), g.sy);
     } else {

@@ -433,8 +433,8 @@ def cas_hypotheses(prev_depth, img_hw, stage_hw, ndepth: int, depth_interval_pix
 
 
 # ---- fast path: bf16 C8 convolution on the tcgen05 tensor cores -----------------------------------
-def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = False) -> torch.Tensor:
-    """fp32 [Cout,Cin,3,3,3] (or [Cin,Cout,3,3,3] when transposed) -> opaque packed bf16 blocks for
+def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = False, act_f16: bool = False) -> torch.Tensor:
+    """fp32 [Cout,Cin,3,3,3] (or [Cin,Cout,3,3,3] when transposed) -> opaque packed bf16 (act_f16: fp16) blocks for
     conv3d_c8 (uint8 tensor on the weight's device)."""
     weight = _f32c(weight.detach())
     _dev(weight)
@@ -445,18 +445,20 @@ def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = 
         raise ValueError(f"unsupported layer shape Cin={cin} Cout={cout} stride={stride}")
     packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
     with torch.cuda.device(weight.device):
-        check(lib().mvs_conv3d_c8_pack_weights(_p(weight), _p(packed), cin, cout, stride, int(transposed), _stream()),
-              "mvs_conv3d_c8_pack_weights")
+        check(lib().mvs_conv3d_c8_pack_weights_ex(_p(weight), _p(packed), cin, cout, stride, int(transposed),
+                                                  L.ACT_F16 if act_f16 else 0, _stream()), "mvs_conv3d_c8_pack_weights")
     return packed
 
 
 def conv3d_c8(x_c8, packed_w, cin: int, cout: int, scale=None, shift=None, skip_c8=None, stride=1, transposed=False,
-              relu=False):
-    """y = [skip +] act(conv(x, w) * scale + shift) on C8 bf16 activations [B,CB,D,H,W,8].
-    Returns C8 bf16 [B,ceil(Cout/8),Do,Ho,Wo,8], or fp32 [B,1,Do,Ho,Wo] when Cout == 1 (`prob`)."""
+              relu=False, act_f16=False):
+    """y = [skip +] act(conv(x, w) * scale + shift) on C8 bf16 activations [B,CB,D,H,W,8] (act_f16: fp16 activations,
+    weights packed with act_f16 -- the 2D feature extractor runs on this with D = 1).
+    Returns C8 [B,ceil(Cout/8),Do,Ho,Wo,8] in the activation dtype, or fp32 [B,1,Do,Ho,Wo] when Cout == 1 (`prob`)."""
     _dev(x_c8, packed_w, scale, shift, skip_c8)
-    if x_c8.dtype != torch.bfloat16 or x_c8.dim() != 6 or x_c8.shape[-1] != 8 or not x_c8.is_contiguous():
-        raise ValueError("x_c8 must be a contiguous C8 bf16 tensor [B,CB,D,H,W,8]")
+    adt = torch.float16 if act_f16 else torch.bfloat16
+    if x_c8.dtype != adt or x_c8.dim() != 6 or x_c8.shape[-1] != 8 or not x_c8.is_contiguous():
+        raise ValueError(f"x_c8 must be a contiguous C8 {adt} tensor [B,CB,D,H,W,8]")
     B, CB, D, H, W, _ = x_c8.shape
     if CB != (cin + 7) // 8:
         raise ValueError(f"x_c8 has {CB} channel blocks, Cin={cin} needs {(cin + 7) // 8}")
@@ -469,11 +471,60 @@ def conv3d_c8(x_c8, packed_w, cin: int, cout: int, scale=None, shift=None, skip_
     if cout == 1:
         y = torch.empty((B, 1, Do, Ho, Wo), dtype=torch.float32, device=x_c8.device)
     else:
-        y = torch.empty((B, (cout + 7) // 8, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=x_c8.device)
-    if skip_c8 is not None and (skip_c8.shape != y.shape or skip_c8.dtype != torch.bfloat16 or not skip_c8.is_contiguous()):
-        raise ValueError("skip_c8 must be a contiguous C8 bf16 tensor of the output's shape")
+        y = torch.empty((B, (cout + 7) // 8, Do, Ho, Wo, 8), dtype=adt, device=x_c8.device)
+    if skip_c8 is not None and (skip_c8.shape != y.shape or skip_c8.dtype != adt or not skip_c8.is_contiguous()):
+        raise ValueError("skip_c8 must be a contiguous C8 tensor of the output's shape and dtype")
     with torch.cuda.device(x_c8.device):
         check(lib().mvs_conv3d_c8_fwd(_p(x_c8), _p(packed_w), _p(scale), _p(shift), _p(skip_c8), _p(y), B, cin, cout, D,
-                                      H, W, stride, int(transposed), L.RELU if relu else 0, _stream()),
-              "mvs_conv3d_c8_fwd")
+                                      H, W, stride, int(transposed), (L.RELU if relu else 0) | (L.ACT_F16 if act_f16 else 0),
+                                      _stream()), "mvs_conv3d_c8_fwd")
     return y
+
+
+# ---- FeatureNet hand-off (SURVEY.md 8(f) f3): the kernels around the extractor's 3x3 convolutions ------------------
+def img_to_c8h(imgs: torch.Tensor) -> torch.Tensor:
+    """[N,3,H,W] uint8 (scaled by 1/255 like the loader) or float32 -> fp16 C8 [N,1,H,W,8], channels 3..7 zero."""
+    _dev(imgs)
+    if imgs.dim() != 4 or imgs.shape[1] != 3 or imgs.dtype not in (torch.uint8, torch.float32):
+        raise ValueError("img_to_c8h takes [N,3,H,W] uint8 or float32 images")
+    imgs = imgs.contiguous()
+    N, _, H, W = imgs.shape
+    out = torch.empty((N, 1, H, W, 8), dtype=torch.float16, device=imgs.device)
+    with torch.cuda.device(imgs.device):
+        check(lib().mvs_img_to_c8h(_p(imgs), L.U8 if imgs.dtype == torch.uint8 else L.F32, _p(out), N, H, W, _stream()),
+              "mvs_img_to_c8h")
+    return out
+
+
+def s2d_c8(x: torch.Tensor) -> torch.Tensor:
+    """2x2 space-to-depth of a C8 map [N,CB,H,W,8] -> [N,4*CB,ceil(H/2),ceil(W/2),8] (block order (py*2+px)*CB + cb)."""
+    _dev(x)
+    if x.dim() != 5 or x.shape[-1] != 8 or x.element_size() != 2 or not x.is_contiguous():
+        raise ValueError("s2d_c8 takes a contiguous C8 map [N,CB,H,W,8]")
+    N, CB, H, W, _ = x.shape
+    out = torch.empty((N, 4 * CB, (H + 1) // 2, (W + 1) // 2, 8), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().mvs_s2d_c8(_p(x), _p(out), N, CB, H, W, _stream()), "mvs_s2d_c8")
+    return out
+
+
+def fpn_merge_c8h(x: torch.Tensor, w_host: torch.Tensor, bias_host, prev=None) -> torch.Tensor:
+    """FPN lateral step: nearest_up2(prev) + conv1x1(x) + bias -> [N,4,H,W,8] fp16.  x [N,Cin/8,H,W,8] fp16 (Cin 8 | 16);
+    w_host [32,Cin] / bias_host [32] float32 CPU tensors (they travel in the kernel parameter block); prev [N,4,Hp,Wp,8]."""
+    _dev(x, prev)
+    if x.dtype != torch.float16 or x.dim() != 5 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous fp16 C8 map [N,CB,H,W,8]")
+    N, CB, H, W, _ = x.shape
+    cin = CB * 8
+    w_host = w_host.detach().to("cpu", torch.float32).reshape(32, cin).contiguous()
+    b_host = None if bias_host is None else bias_host.detach().to("cpu", torch.float32).reshape(32).contiguous()
+    Hp = Wp = 0
+    if prev is not None:
+        if prev.dtype != torch.float16 or prev.dim() != 5 or prev.shape[:2] != (N, 4) or not prev.is_contiguous():
+            raise ValueError("prev must be a contiguous fp16 C8 map [N,4,Hp,Wp,8]")
+        Hp, Wp = prev.shape[2:4]
+    out = torch.empty((N, 4, H, W, 8), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().mvs_fpn_merge_c8h(_p(x), _p(w_host), _p(b_host), _p(prev), _p(out), N, cin, H, W, Hp, Wp, _stream()),
+              "mvs_fpn_merge_c8h")
+    return out

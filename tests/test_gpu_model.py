@@ -38,18 +38,71 @@ def test_featurenet_mirror_strict_and_fast_vs_reference_golden():
     net.load_state_dict(_sd(cases.featurenet_state(33)), strict=True)
     with torch.no_grad():
         strict = net(img, mode="strict")
-        fast = net(img, mode="fast")
-        c8h = net(img, mode="fast", emit_c8h=True)
-    for k, c in (("stage1", 32), ("stage2", 16), ("stage3", 8)):
-        g = gold[k]
-        np.testing.assert_allclose(strict[k].cpu().numpy(), g, rtol=2e-5, atol=2e-5)        # fp32 cuDNN vs fp32 oneDNN
-        f = fast[k].float().cpu().numpy()
-        assert np.abs(f - g).max() <= 2e-2 * np.abs(g).max(), (k, np.abs(f - g).max(), np.abs(g).max())   # fp16 activations
-        # the C8H emission is a pure re-layout of the fast output
-        B, CB, h, w, _ = c8h[k].shape
-        assert (B, CB * 8, h, w) == tuple(fast[k].shape) and c8h[k].dtype == torch.float16 and c8h[k].is_contiguous()
-        back = c8h[k].permute(0, 1, 4, 2, 3).reshape(B, c, h, w)
-        assert torch.equal(back, fast[k])
+    for k in ("stage1", "stage2", "stage3"):
+        np.testing.assert_allclose(strict[k].cpu().numpy(), gold[k], rtol=2e-5, atol=2e-5)  # fp32 cuDNN vs fp32 oneDNN
+    for engine in ("native", "torch"):
+        # native: tcgen05 3x3 layers (D = 1, fp16 C8), space-to-depth 5x5/s2 layers, fused FPN laterals; torch: cuDNN fp16
+        net.engine = engine
+        with torch.no_grad():
+            fast = net(img, mode="fast")
+            c8h = net(img, mode="fast", emit_c8h=True)
+            f32in = net(img.float() / 255.0, mode="fast")              # float images as the reference's loader hands them
+        for k, c in (("stage1", 32), ("stage2", 16), ("stage3", 8)):
+            g = gold[k]
+            f = fast[k].float().cpu().numpy()
+            err = np.abs(f - g).max() / np.abs(g).max()
+            print(engine, k, "max err / max |ref|", err)
+            assert err <= 1e-2, (engine, k, err)                       # fp16 activations through 8-9 layers
+            assert torch.equal(f32in[k], fast[k])                      # uint8 hand-off == float hand-off
+            # the C8H emission is a pure re-layout of the fast output
+            B, CB, h, w, _ = c8h[k].shape
+            assert (B, CB * 8, h, w) == tuple(fast[k].shape) and c8h[k].dtype == torch.float16 and c8h[k].is_contiguous()
+            back = c8h[k].permute(0, 1, 4, 2, 3).reshape(B, c, h, w)
+            assert torch.equal(back, fast[k])
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 8, 21, 150), (32, 16, 12, 70), (64, 32, 9, 40), (32, 8, 16, 133), (16, 16, 7, 64)])
+def test_conv2d_on_the_tcgen05_kernel_fp16(cin, cout, H, W):
+    """The extractor's 3x3 layers: mvs_conv3d_c8_fwd with D = 1 and MVS_ACT_F16 vs torch conv2d on fp16-rounded operands."""
+    from mvs_b200 import ops
+    from mvs_b200.featurenet import _as_3x3x3
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    x = torch.randn(2, cin, H, W, generator=g).half().float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).half().float()
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x.double(), w.double(), padding=1) * scale.view(1, -1, 1, 1).double() + shift.view(1, -1, 1, 1).double()).float()
+    xc = ops.pack_c8(x.to(DEV), torch.float16).view(2, cin // 8, 1, H, W, 8)
+    packed = ops.pack_conv_weights(_as_3x3x3(w.to(DEV)), 1, False, act_f16=True)
+    y = ops.conv3d_c8(xc, packed, cin, cout, scale.to(DEV), shift.to(DEV), None, 1, False, True, act_f16=True)
+    assert y.dtype == torch.float16 and tuple(y.shape) == (2, (cout + 7) // 8, 1, H, W, 8)
+    out = y.view(2, -1, H, W, 8).permute(0, 1, 4, 2, 3).reshape(2, -1, H, W)[:, :cout].float().cpu()
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=2 ** -10, atol=2e-3)
+
+
+def test_s2d_and_fpn_merge_kernels():
+    from mvs_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 16, 13, 22, generator=g).half()
+    xc = ops.pack_c8(x.float().to(DEV), torch.float16)                                # [3,2,13,22,8]
+    s = ops.s2d_c8(xc)
+    assert tuple(s.shape) == (3, 8, 7, 11, 8)
+    nchw = s.permute(0, 1, 4, 2, 3).reshape(3, 64, 7, 11).cpu()
+    xp = F.pad(x, (0, 0, 0, 1))                                                        # odd height: zero row
+    for py in range(2):
+        for px in range(2):
+            assert torch.equal(nchw[:, (py * 2 + px) * 16:(py * 2 + px + 1) * 16], xp[:, :, py::2, px::2])
+    # lateral: nearest_up2(prev) + conv1x1(x) + bias
+    prev = torch.randn(3, 32, 7, 11, generator=g).half()
+    w, b = torch.randn(32, 16, generator=g) / 4, torch.randn(32, generator=g) * 0.1
+    ref = F.interpolate(prev.float(), scale_factor=2, mode="nearest")[:, :, :13] + F.conv2d(x.float(), w.view(32, 16, 1, 1), b)
+    out = ops.fpn_merge_c8h(xc, w, b, ops.pack_c8(prev.float().to(DEV), torch.float16))
+    got = out.permute(0, 1, 4, 2, 3).reshape(3, 32, 13, 22).float().cpu()
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2 ** -10, atol=1e-3)
+    u8 = torch.randint(0, 256, (2, 3, 9, 17), dtype=torch.uint8, generator=g)
+    c = ops.img_to_c8h(u8.to(DEV)).cpu()
+    assert torch.equal(c[:, 0, :, :, :3].permute(0, 3, 1, 2), (u8.float() / 255.0).half()) and not c[..., 3:].any()
 
 
 @pytest.mark.parametrize("mode", ["strict", "fast"])
