@@ -133,9 +133,16 @@ int mvs_pack_c8h(const void *src, int src_dtype, void *dst_c8h, int B, int C, in
  *                      w_host [32,Cin] / bias_host [32] are HOST pointers (copied into the kernel parameter block);
  *                      prev [N,4,Hp,Wp,8] or NULL; out [N,4,H,W,8]; all maps fp16 C8. */
 int mvs_img_to_c8h(const void *img, int src_dtype, void *dst_c8h, int N, int H, int W, void *stream);
-int mvs_s2d_c8(const void *src_c8, void *dst_c8, int N, int CB, int H, int W, void *stream);
+/* Map layouts (flags): batch-major [N][CB][H][W][8] (default; what the builder takes) or "folded" [CB][N][H][W][8] = the
+ * bytes mvs_conv3d_c8_fwd reads as ONE volume [1][CB][D=N][H][W][8], so the N images ride the row axis of the convolution.
+ *   mvs_s2d_c8: MVS_MAP_SRC_FOLDED, MVS_MAP_DST_FOLDED;  mvs_fpn_merge_c8h: MVS_MAP_SRC_FOLDED (x), MVS_MAP_DST_FOLDED (out),
+ *   MVS_MAP_PREV_FOLDED (prev). */
+#define MVS_MAP_SRC_FOLDED 1
+#define MVS_MAP_DST_FOLDED 2
+#define MVS_MAP_PREV_FOLDED 4
+int mvs_s2d_c8(const void *src_c8, void *dst_c8, int N, int CB, int H, int W, int flags, void *stream);
 int mvs_fpn_merge_c8h(const void *x_c8h, const float *w_host, const float *bias_host, const void *prev_c8h,
-                      void *out_c8h, int N, int Cin, int H, int W, int Hp, int Wp, void *stream);
+                      void *out_c8h, int N, int Cin, int H, int W, int Hp, int Wp, int flags, void *stream);
 
 /* ---- a3: 3x3x3 convolution + folded BatchNorm + ReLU + skip ------------------------------------
  * Replaces ConvBnReLU3D / Conv3d / Deconv3d blocks and the skip adds of CostRegNet.forward:
@@ -150,6 +157,13 @@ int mvs_fpn_merge_c8h(const void *x_c8h, const float *w_host, const float *bias_
 int mvs_conv3d_fwd(const float *x, const float *w, const float *scale, const float *shift,
                    const float *skip, float *y, int B, int Cin, int Cout, int D, int H, int W,
                    int stride, int transposed, int flags, void *stream);
+
+/* Weight gradient of the same layer (training: loss.backward(), CasMVSNet/train.py:165-170): strict fp32.
+ * x [B,Cin,D,H,W] (the layer's input), grad_y = dL/dy (the layer's output extents) -> gw [Cout,Cin,3,3,3]
+ * (transposed: [Cin,Cout,3,3,3]).  gw must be ZERO on entry (CTAs accumulate with atomicAdd).  The DATA gradient needs no
+ * entry point of its own: d/dx of a (strided) convolution is mvs_conv3d_fwd(grad_y, w, transposed = !transposed). */
+int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, int B, int Cin, int Cout, int D, int H, int W,
+                     int stride, int transposed, void *stream);
 
 /* Fast variant: C8 bf16 activations, tcgen05 (UMMA) implicit GEMM, operands staged in shared memory by the TMA engine
  * (1-D bulk copies per staged line in the stride-1 layers, cp.async in the stride-2 / transposed layers), TMEM

@@ -50,9 +50,10 @@ SIGNATURES = {
     "mvs_unpack_c8": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp]),
     "mvs_pack_c8h": (_i, [_vp, _i, _vp, _i, _i, _i64, _vp]),
     "mvs_img_to_c8h": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
-    "mvs_s2d_c8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "mvs_fpn_merge_c8h": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
+    "mvs_s2d_c8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mvs_fpn_merge_c8h": (_i, [_vp] * 5 + [_i] * 7 + [_vp]),
     "mvs_conv3d_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
+    "mvs_conv3d_wgrad": (_i, [_vp] * 3 + [_i] * 8 + [_vp]),
     "mvs_conv3d_c8_packed_weight_bytes": (_i64, [_i] * 4),
     "mvs_conv3d_c8_pack_weights": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
     "mvs_conv3d_c8_pack_weights_ex": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),

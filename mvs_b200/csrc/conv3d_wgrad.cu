@@ -1,0 +1,123 @@
+// Weight gradient of the 3x3x3 convolutions (training step, BASELINE configs[3]): strict fp32.
+//   conv      y[co,o] = sum_{ci,k} w[co,ci,k] x[ci, s*o + k - 1]        gw[co,ci,k] = sum_{n,o} gy[n,co,o] x[n,ci, s*o + k - 1]
+//   transposed y[co, s*i + k - 1] += w[ci,co,k] x[ci,i]                   gw[ci,co,k] = sum_{n,i} x[n,ci,i] gy[n,co, s*i + k - 1]
+// Both are G[a][b][k] = sum_{n,p} A[n,a,p] * T[n,b, s*p + k - 1] with (A, T) = (gy, x) or (x, gy): one kernel.
+// Replaces the wgrad half of autograd through nn.Conv3d / nn.ConvTranspose3d (CasMVSNet/models/module.py:137,180,
+// MVSNet/models/module.py:29, CVP-MVSNet/models/net.py:56-76) under loss.backward() (CasMVSNet/train.py:165-170).
+//
+// A CTA owns an 8 x 8 block of (a, b) channel pairs and a contiguous chunk of A's (n, d, h) rows; it walks the rows in
+// 64-position W segments, staging the A segment and the nine (kd, kh) T rows (with their kw halo) in shared memory.
+// Thread = (pair, lane of 4): 27 accumulators in registers over positions w = lane, lane + 4, ...; at the end the four
+// lanes are reduced by shuffles and the CTA adds its 64 x 27 partial sums to gw with atomicAdd (the accumulation order
+// over CTAs is therefore not deterministic in the last bits, like cuDNN's default wgrad algorithms).
+#include "common.cuh"
+
+namespace mvs {
+
+constexpr int WG_SEG = 64;
+
+template <int S>
+__global__ void __launch_bounds__(256)
+conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, float *__restrict__ G, int N, int Ca, int Cb,
+                    int Da, int Ha, int Wa, int Dt, int Ht, int Wt, int rows_per_cta)
+{
+    constexpr int TW = S * WG_SEG + 2;                 // staged T positions per row: s*w + kw - 1 for w < 64, kw < 3
+    constexpr int TP = S == 1 ? 72 : 136;              // padded row pitch (pitch mod 32 == 8: conflict-free for 8 b x 4 lanes)
+    __shared__ float sA[8][WG_SEG];
+    __shared__ float sT[8][9][TP];
+    const int tid = threadIdx.x, pair = tid >> 2, lane = tid & 3;
+    const int a_loc = pair >> 3, b_loc = pair & 7;
+    const int a0 = blockIdx.y * 8, b0 = blockIdx.z * 8;
+    const long long total_rows = (long long)N * Da * Ha;
+    const long long row_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long row_end = min(row_begin + rows_per_cta, total_rows);
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    const size_t avol = (size_t)Da * Ha * Wa, tvol = (size_t)Dt * Ht * Wt;
+
+    for (long long row = row_begin; row < row_end; ++row) {
+        const int h = (int)(row % Ha);
+        const int d = (int)((row / Ha) % Da);
+        const int n = (int)(row / ((long long)Ha * Da));
+        for (int w0 = 0; w0 < Wa; w0 += WG_SEG) {
+            __syncthreads();
+            // A segment: 8 channels x 64 positions
+            for (int i = tid; i < 8 * WG_SEG; i += 256) {
+                const int c = i / WG_SEG, w = i % WG_SEG;
+                const int a = a0 + c;
+                sA[c][w] = (a < Ca && w0 + w < Wa) ? __ldg(A + ((size_t)n * Ca + a) * avol + ((size_t)d * Ha + h) * Wa + w0 + w) : 0.f;
+            }
+            // T rows: 8 channels x 9 (kd, kh) rows x (S*64 + 2) positions starting at S*w0 - 1
+            for (int i = tid; i < 8 * 9 * TW; i += 256) {
+                const int j = i % TW, r = (i / TW) % 9, c = i / (TW * 9);
+                const int b = b0 + c;
+                const int td = S * d + r / 3 - 1, th = S * h + r % 3 - 1, tw = S * w0 - 1 + j;
+                const bool ok = b < Cb && td >= 0 && td < Dt && th >= 0 && th < Ht && tw >= 0 && tw < Wt;
+                sT[c][r][j] = ok ? __ldg(T + ((size_t)n * Cb + b) * tvol + ((size_t)td * Ht + th) * Wt + tw) : 0.f;
+            }
+            __syncthreads();
+            const int wn = min(WG_SEG, Wa - w0);
+            for (int w = lane; w < wn; w += 4) {
+                const float av = sA[a_loc][w];
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+                    const float *t = &sT[b_loc][r][S * w];
+                    acc[r * 3 + 0] = fmaf(av, t[0], acc[r * 3 + 0]);
+                    acc[r * 3 + 1] = fmaf(av, t[1], acc[r * 3 + 1]);
+                    acc[r * 3 + 2] = fmaf(av, t[2], acc[r * 3 + 2]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        float v = acc[k];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        acc[k] = v;
+    }
+    const int a = a0 + a_loc, b = b0 + b_loc;
+    if (lane == 0 && a < Ca && b < Cb) {
+        float *g = G + ((size_t)a * Cb + b) * 27;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) atomicAdd(g + k, acc[k]);
+    }
+}
+
+}  // namespace mvs
+
+using namespace mvs;
+
+// gw must be zero-initialised by the caller (the kernel accumulates with atomicAdd).
+extern "C" int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, int B, int Cin, int Cout, int D, int H, int W,
+                                int stride, int transposed, void *stream)
+{
+    if (B == 0 || D == 0 || H == 0 || W == 0) return MVS_OK;
+    MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "extents must be positive");
+    MVS_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
+    MVS_REQUIRE(x && grad_y && gw, "null pointer");
+    int Do, Ho, Wo;
+    if (transposed) { Do = D * stride; Ho = H * stride; Wo = W * stride; }
+    else { Do = (D - 1) / stride + 1; Ho = (H - 1) / stride + 1; Wo = (W - 1) / stride + 1; }
+    // (A, T): conv: (grad_y [Cout, out extents], x [Cin, in extents]); transposed: (x [Cin, in], grad_y [Cout, out])
+    const float *A = transposed ? x : grad_y, *T = transposed ? grad_y : x;
+    const int Ca = transposed ? Cin : Cout, Cb = transposed ? Cout : Cin;
+    const int Da = transposed ? D : Do, Ha = transposed ? H : Ho, Wa = transposed ? W : Wo;
+    const int Dt = transposed ? Do : D, Ht = transposed ? Ho : H, Wt = transposed ? Wo : W;
+    const long long rows = (long long)B * Da * Ha;
+    const int pair_blocks = cdiv(Ca, 8) * cdiv(Cb, 8);
+    // ~16 CTAs per SM in total: enough parallelism, few enough CTAs that the final atomics stay cheap
+    long long chunks = (16LL * sm_count() + pair_blocks - 1) / pair_blocks;
+    if (chunks > rows) chunks = rows;
+    if (chunks < 1) chunks = 1;
+    const int rows_per_cta = (int)((rows + chunks - 1) / chunks);
+    dim3 grid((unsigned)cdiv(rows, rows_per_cta), cdiv(Ca, 8), cdiv(Cb, 8));
+    MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "too many channel blocks");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 1)
+        conv3d_wgrad_kernel<1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    else
+        conv3d_wgrad_kernel<2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    return check_launch("mvs_conv3d_wgrad");
+}

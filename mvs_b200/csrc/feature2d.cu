@@ -29,19 +29,28 @@ img_to_c8h_kernel(const void *__restrict__ img, int is_u8, uint4 *__restrict__ d
     dst[(size_t)n * plane + i] = make_uint4(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b), 0u, 0u);
 }
 
+// Map layouts: "batch-major" [N][CB][H][W][8] (what the builder takes, one contiguous map per view) or "folded"
+// [CB][N][H][W][8] -- the SAME bytes the tcgen05 convolution reads as ONE volume [B=1][CB][D=N][H][W][8], so that the N images
+// of a reference view ride the kernel's row axis (3D weights populated in the kd = 1 slice only: no mixing between images)
+// instead of being N one-row volumes: 2-3x fewer pipeline steps per pixel (profiles/r2c_launches.csv vs r2d).
+__device__ __forceinline__ size_t map_plane(int n, int cb, int N, int CB, bool folded)
+{
+    return folded ? (size_t)cb * N + n : (size_t)n * CB + cb;
+}
+
 // dst[n][(py*2+px)*CB + cb][y][x] = src[n][cb][2y+py][2x+px]  (zero outside)
 __global__ void __launch_bounds__(256)
-s2d_c8_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int CB, int H, int W, int Ho, int Wo)
+s2d_c8_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int N, int CB, int H, int W, int Ho, int Wo, int flags)
 {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= Wo || y >= Ho) return;
     const int n = blockIdx.z / CB, cb = blockIdx.z % CB;
-    const uint4 *s = src + ((size_t)n * CB + cb) * H * W;
+    const uint4 *s = src + map_plane(n, cb, N, CB, flags & 1) * H * W;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int yy = 2 * y + (p >> 1), xx = 2 * x + (p & 1);
         const uint4 v = (yy < H && xx < W) ? __ldg(s + (size_t)yy * W + xx) : make_uint4(0, 0, 0, 0);
-        dst[(((size_t)n * 4 * CB + (size_t)p * CB + cb) * Ho + y) * Wo + x] = v;
+        dst[(map_plane(n, p * CB + cb, N, 4 * CB, flags & 2) * Ho + y) * Wo + x] = v;
     }
 }
 
@@ -60,15 +69,15 @@ __device__ __forceinline__ uint32_t f2h(float a, float b)
 template <int CIN>
 __global__ void __launch_bounds__(128)
 fpn_merge_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ prev, uint4 *__restrict__ out,
-                 const __grid_constant__ Lateral L, int H, int W, int Hp, int Wp)
+                 const __grid_constant__ Lateral L, int H, int W, int Hp, int Wp, int flags)
 {
-    const int px = blockIdx.x * 128 + threadIdx.x, py = blockIdx.y, n = blockIdx.z;
+    const int px = blockIdx.x * 128 + threadIdx.x, py = blockIdx.y, n = blockIdx.z, N = gridDim.z;
     if (px >= W) return;
     const size_t plane = (size_t)H * W, pix = (size_t)py * W + px;
     float xin[CIN];
 #pragma unroll
     for (int cb = 0; cb < CIN / 8; ++cb) {
-        const uint4 v = __ldg(x + ((size_t)n * (CIN / 8) + cb) * plane + pix);
+        const uint4 v = __ldg(x + map_plane(n, cb, N, CIN / 8, flags & 1) * plane + pix);
         const float2 a = h2f(v.x), b = h2f(v.y), c = h2f(v.z), d = h2f(v.w);
         xin[cb * 8 + 0] = a.x; xin[cb * 8 + 1] = a.y; xin[cb * 8 + 2] = b.x; xin[cb * 8 + 3] = b.y;
         xin[cb * 8 + 4] = c.x; xin[cb * 8 + 5] = c.y; xin[cb * 8 + 6] = d.x; xin[cb * 8 + 7] = d.y;
@@ -85,11 +94,11 @@ fpn_merge_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ prev, ui
             acc[k] = a;
         }
         if (prev) {                 // F.interpolate(scale_factor=2, mode="nearest"): src index = floor(dst / 2)
-            const uint4 p = __ldg(prev + ((size_t)n * 4 + ob) * pplane + ppix);
+            const uint4 p = __ldg(prev + map_plane(n, ob, N, 4, flags & 4) * pplane + ppix);
             const float2 a = h2f(p.x), b = h2f(p.y), c = h2f(p.z), d = h2f(p.w);
             acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
         }
-        out[((size_t)n * 4 + ob) * plane + pix] = make_uint4(f2h(acc[0], acc[1]), f2h(acc[2], acc[3]), f2h(acc[4], acc[5]), f2h(acc[6], acc[7]));
+        out[map_plane(n, ob, N, 4, flags & 2) * plane + pix] = make_uint4(f2h(acc[0], acc[1]), f2h(acc[2], acc[3]), f2h(acc[4], acc[5]), f2h(acc[6], acc[7]));
     }
 }
 
@@ -108,19 +117,19 @@ extern "C" int mvs_img_to_c8h(const void *img, int src_dtype, void *dst_c8h, int
     return check_launch("mvs_img_to_c8h");
 }
 
-extern "C" int mvs_s2d_c8(const void *src_c8, void *dst_c8, int N, int CB, int H, int W, void *stream)
+extern "C" int mvs_s2d_c8(const void *src_c8, void *dst_c8, int N, int CB, int H, int W, int flags, void *stream)
 {
     if (N == 0 || CB == 0 || H == 0 || W == 0) return MVS_OK;
     MVS_REQUIRE(N > 0 && CB > 0 && H > 0 && W > 0 && (long long)N * CB <= 65535, "bad extents");
     MVS_REQUIRE(src_c8 && dst_c8, "null pointer");
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     MVS_REQUIRE(cdiv(Ho, 4) <= 65535, "H too large");
-    s2d_c8_kernel<<<dim3(cdiv(Wo, 64), cdiv(Ho, 4), N * CB), 256, 0, (cudaStream_t)stream>>>((const uint4 *)src_c8, (uint4 *)dst_c8, CB, H, W, Ho, Wo);
+    s2d_c8_kernel<<<dim3(cdiv(Wo, 64), cdiv(Ho, 4), N * CB), 256, 0, (cudaStream_t)stream>>>((const uint4 *)src_c8, (uint4 *)dst_c8, N, CB, H, W, Ho, Wo, flags);
     return check_launch("mvs_s2d_c8");
 }
 
 extern "C" int mvs_fpn_merge_c8h(const void *x_c8h, const float *w_host, const float *bias_host, const void *prev_c8h,
-                                 void *out_c8h, int N, int Cin, int H, int W, int Hp, int Wp, void *stream)
+                                 void *out_c8h, int N, int Cin, int H, int W, int Hp, int Wp, int flags, void *stream)
 {
     if (N == 0 || H == 0 || W == 0) return MVS_OK;
     MVS_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535 && H <= 65535, "bad extents");
@@ -135,8 +144,8 @@ extern "C" int mvs_fpn_merge_c8h(const void *x_c8h, const float *w_host, const f
     }
     dim3 grid(cdiv(W, 128), H, N);
     if (Cin == 8)
-        fpn_merge_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint4 *)x_c8h, (const uint4 *)prev_c8h, (uint4 *)out_c8h, L, H, W, Hp, Wp);
+        fpn_merge_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint4 *)x_c8h, (const uint4 *)prev_c8h, (uint4 *)out_c8h, L, H, W, Hp, Wp, flags);
     else
-        fpn_merge_kernel<16><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint4 *)x_c8h, (const uint4 *)prev_c8h, (uint4 *)out_c8h, L, H, W, Hp, Wp);
+        fpn_merge_kernel<16><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint4 *)x_c8h, (const uint4 *)prev_c8h, (uint4 *)out_c8h, L, H, W, Hp, Wp, flags);
     return check_launch("mvs_fpn_merge_c8h");
 }

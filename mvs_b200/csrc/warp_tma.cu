@@ -34,6 +34,9 @@
 
 namespace mvs {
 
+#ifndef MVS_TMA_CHAIN
+#define MVS_TMA_CHAIN 0      // 1: chain every gather to the previous blend (one tap block in flight per warp)
+#endif
 constexpr int TMA_MAX_SRC = 6;        // source views the TMA path takes (smem: 2 buffers x NSRC slots); more -> gather kernel
 constexpr int TMA_THREADS = 512;
 constexpr int TILE_W = 32, TILE_H = 16;
@@ -376,7 +379,9 @@ warp_variance_tma_kernel(const uint4 *__restrict__ ref, SrcPtrs srcs, const floa
                     slow_taps<PL, AC>(t, cams[v], g, fx, fy, load_depth(d), (const uint4 *)srcs.p[v] + ((size_t)cur.b * CB + cb) * plane, H, W);
                 }
                 blend_accumulate(t, st, sum, sq);
+#if MVS_TMA_CHAIN
                 asm volatile("and.b32 %0, %1, 0;\n" : "=r"(dep) : "r"(__float_as_uint(sum[3].y)));
+#endif
             };
             auto finish = [&](int d, const float2 (&sum)[4], const float2 (&sq)[4], bool bad) {
                 uint32_t o4[4];
@@ -475,8 +480,8 @@ static BoxGeom box_geom(int nsrc, int dch)
 {
     BoxGeom b;
     const int slot_px = (220 * 1024 / (2 * nsrc) / 16) & ~7;
-    const int wide_h = dch >= 8 ? 27 : (dch >= 4 ? 24 : 22), tall_w = dch >= 8 ? 40 : 36;
-    int want_px = dch >= 8 ? 1760 : (dch >= 4 ? 1184 : 960);
+    const int wide_h = dch >= 8 ? 27 : (dch >= 4 ? 24 : 22), tall_w = dch >= 8 ? 44 : 40;
+    int want_px = dch >= 8 ? 1760 : (dch >= 4 ? 1280 : 960);
     if (want_px > slot_px) want_px = slot_px;
     b.bw[0] = want_px / wide_h; if (b.bw[0] > 96) b.bw[0] = 96;
     b.bh[0] = wide_h;

@@ -145,8 +145,14 @@ class _NativeLayer:
             self.key = key
         return self
 
-    def __call__(self, x):          # x [N,CB,H,W,8] fp16 -> [N,Cout/8,H,W,8]
+    def __call__(self, x, folded=False):
+        """x [N,CB,H,W,8] fp16 -> [N,Cout/8,H,W,8]; folded: x [CB,N,H,W,8] -> [Cout/8,N,H,W,8], run as ONE volume with
+        D = N (the 3D weights live in the kd = 1 slice only, so images do not mix)."""
         L = self.get()
+        if folded:
+            CB, N, H, W, _ = x.shape
+            y = ops.conv3d_c8(x.view(1, CB, N, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu, act_f16=True)
+            return y.view(y.shape[1], N, H, W, 8)
         N, CB, H, W, _ = x.shape
         y = ops.conv3d_c8(x.view(N, CB, 1, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu, act_f16=True)
         return y.view(N, y.shape[1], H, W, 8)
@@ -248,15 +254,18 @@ class FeatureNet(nn.Module):
                 nv["lateral"] = (lk, [t.detach().float().cpu() for t in (self.inner1.weight, self.inner1.bias, self.inner2.weight, self.inner2.bias)])
         w1, b1, w2, b2 = nv["lateral"][1]
         L = nv["blocks"]
-        t = ops.img_to_c8h(x)                                     # [N,1,H,W,8]
-        conv0 = L[1](L[0](t))
-        conv1 = L[4](L[3](L[2](ops.s2d_c8(conv0))))
-        conv2 = L[7](L[6](L[5](ops.s2d_c8(conv1))))
+        # The full- and half-resolution layers run FOLDED ([CB,N,H,W,8] = one volume with D = N images on the convolution's
+        # row axis); maps with one channel block have the same bytes in both layouts, the builder's inputs are batch-major.
+        N = x.shape[0]
+        t = ops.img_to_c8h(x).view(1, N, *x.shape[2:], 8)         # [1,N,H,W,8]: CB = 1, folded == batch-major
+        conv0 = L[1](L[0](t, True), True)                         # [1,N,H,W,8]
+        conv1 = L[4](L[3](L[2](ops.s2d_c8(conv0, True, True), True), True), True)          # [2,N,H/2,W/2,8] folded
+        conv2 = L[7](L[6](L[5](ops.s2d_c8(conv1, True, False))))                           # [N,4,H/4,W/4,8] batch-major
         out = {"stage1": nv["out1"](conv2)}
-        intra = ops.fpn_merge_c8h(conv1, w1, b1, conv2)
+        intra = ops.fpn_merge_c8h(conv1, w1, b1, conv2, x_folded=True)                     # [N,4,H/2,W/2,8]
         out["stage2"] = nv["out2"](intra)
-        intra = ops.fpn_merge_c8h(conv0, w2, b2, intra)
-        out["stage3"] = nv["out3"](intra)
+        intra = ops.fpn_merge_c8h(conv0, w2, b2, intra, x_folded=True, out_folded=True)    # [4,N,H,W,8] folded
+        out["stage3"] = nv["out3"](intra, True).view(N, 1, *x.shape[2:], 8)                # [1,N,..] == [N,1,..]
         return out                                                # C8H [N,C/8,h,w,8] fp16
 
     def forward(self, x, mode=None, emit_c8h=False):

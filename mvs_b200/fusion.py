@@ -150,3 +150,39 @@ def backproject(depth_est_averaged, valid_points, ref_intrinsics, ref_extrinsics
         check(lib().mvs_geo_backproject(_p(d), _p(m), _p(cam), _p(xyz), H, W, _stream()), "mvs_geo_backproject")
     pts = xyz[m.bool()]
     return _out(pts, as_np)
+
+
+def filter_depth(depths, confidences, intrinsics, extrinsics, pairs, images=None, plyfilename=None, conf_thresh=0.8,
+                 min_views=3, dist_thresh=1.0, rel_thresh=0.01):
+    """The body of `filter_depth` (MVSNet/eval.py:212-326, CasMVSNet/test.py:297-410) WITHOUT the trip through the file
+    system: the reference re-reads every depth / confidence map it has just written as .pfm (eval.py:232-236, 246) and
+    loops over (ref, src) pairs in NumPy; here the maps stay on the device (feed `cascade_hot_path` / `CascadeMVSNet`
+    outputs straight in), every reference view is ONE fused launch + one back-projection launch.
+
+    depths / confidences: per-view [H,W] maps (NumPy or CUDA tensors); intrinsics / extrinsics: per-view 3x3 / 4x4;
+    pairs: [(ref_view, [src_views...])] as `read_pair_file` returns; images: optional per-view [H,W,3] float in [0,1]
+    ALREADY at the depth maps' resolution (the reference hard-codes a DTU crop `ref_img[1:-16:4, 1::4]`, eval.py:301).
+    Returns (vertexs float32 [N,3], vertex_colors uint8 [N,3], per-view dicts); writes the PLY when `plyfilename` is given."""
+    from . import io as mio
+    vertexs, vertex_colors, per_view = [], [], []
+    for ref_view, src_views in pairs:
+        out = fuse_ref_view(depths[ref_view], confidences[ref_view], intrinsics[ref_view], extrinsics[ref_view],
+                            [depths[s] for s in src_views], [intrinsics[s] for s in src_views],
+                            [extrinsics[s] for s in src_views], conf_thresh=conf_thresh, min_views=min_views,
+                            dist_thresh=dist_thresh, rel_thresh=rel_thresh)
+        pts = backproject(out["depth_est_averaged"], out["final_mask"], intrinsics[ref_view], extrinsics[ref_view])
+        pts = pts.cpu().numpy() if isinstance(pts, torch.Tensor) else pts
+        fm = out["final_mask"].cpu().numpy() if isinstance(out["final_mask"], torch.Tensor) else out["final_mask"]
+        vertexs.append(np.asarray(pts, np.float32))
+        if images is not None:
+            img = images[ref_view]
+            img = img.cpu().numpy() if isinstance(img, torch.Tensor) else np.asarray(img)
+            vertex_colors.append((img[fm] * 255).astype(np.uint8))           # eval.py:306
+        else:
+            vertex_colors.append(np.full((len(pts), 3), 255, np.uint8))
+        per_view.append(out)
+    vertexs = np.concatenate(vertexs, axis=0) if vertexs else np.zeros((0, 3), np.float32)
+    vertex_colors = np.concatenate(vertex_colors, axis=0) if vertex_colors else np.zeros((0, 3), np.uint8)
+    if plyfilename is not None:
+        mio.write_ply(plyfilename, vertexs, vertex_colors)
+    return vertexs, vertex_colors, per_view

@@ -496,35 +496,46 @@ def img_to_c8h(imgs: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def s2d_c8(x: torch.Tensor) -> torch.Tensor:
-    """2x2 space-to-depth of a C8 map [N,CB,H,W,8] -> [N,4*CB,ceil(H/2),ceil(W/2),8] (block order (py*2+px)*CB + cb)."""
-    _dev(x)
+def _map_dims(x, folded):
+    """(N, CB, H, W) of a C8 map in batch-major [N,CB,H,W,8] or folded [CB,N,H,W,8] layout."""
     if x.dim() != 5 or x.shape[-1] != 8 or x.element_size() != 2 or not x.is_contiguous():
-        raise ValueError("s2d_c8 takes a contiguous C8 map [N,CB,H,W,8]")
-    N, CB, H, W, _ = x.shape
-    out = torch.empty((N, 4 * CB, (H + 1) // 2, (W + 1) // 2, 8), dtype=x.dtype, device=x.device)
+        raise ValueError("expected a contiguous C8 map [N,CB,H,W,8] (folded: [CB,N,H,W,8])")
+    a, b, H, W, _ = x.shape
+    return (b, a, H, W) if folded else (a, b, H, W)
+
+
+def s2d_c8(x: torch.Tensor, src_folded=False, dst_folded=False) -> torch.Tensor:
+    """2x2 space-to-depth of a C8 map [N,CB,H,W,8] -> [N,4*CB,ceil(H/2),ceil(W/2),8] (block order (py*2+px)*CB + cb).
+    `*_folded`: the map is laid out [CB,N,H,W,8] (one volume [1,CB,D=N,H,W,8] for the convolution kernel)."""
+    _dev(x)
+    N, CB, H, W = _map_dims(x, src_folded)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    out = torch.empty((4 * CB, N, Ho, Wo, 8) if dst_folded else (N, 4 * CB, Ho, Wo, 8), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib().mvs_s2d_c8(_p(x), _p(out), N, CB, H, W, _stream()), "mvs_s2d_c8")
+        check(lib().mvs_s2d_c8(_p(x), _p(out), N, CB, H, W, (1 if src_folded else 0) | (2 if dst_folded else 0), _stream()), "mvs_s2d_c8")
     return out
 
 
-def fpn_merge_c8h(x: torch.Tensor, w_host: torch.Tensor, bias_host, prev=None) -> torch.Tensor:
+def fpn_merge_c8h(x: torch.Tensor, w_host: torch.Tensor, bias_host, prev=None, x_folded=False, out_folded=False,
+                  prev_folded=False) -> torch.Tensor:
     """FPN lateral step: nearest_up2(prev) + conv1x1(x) + bias -> [N,4,H,W,8] fp16.  x [N,Cin/8,H,W,8] fp16 (Cin 8 | 16);
-    w_host [32,Cin] / bias_host [32] float32 CPU tensors (they travel in the kernel parameter block); prev [N,4,Hp,Wp,8]."""
+    w_host [32,Cin] / bias_host [32] float32 CPU tensors (they travel in the kernel parameter block: pass CPU copies, a
+    CUDA tensor would cost a device->host sync per call); prev [N,4,Hp,Wp,8].  `*_folded`: [CB,N,H,W,8] layouts."""
     _dev(x, prev)
-    if x.dtype != torch.float16 or x.dim() != 5 or not x.is_contiguous():
-        raise ValueError("x must be a contiguous fp16 C8 map [N,CB,H,W,8]")
-    N, CB, H, W, _ = x.shape
+    if x.dtype != torch.float16:
+        raise ValueError("x must be an fp16 C8 map")
+    N, CB, H, W = _map_dims(x, x_folded)
     cin = CB * 8
     w_host = w_host.detach().to("cpu", torch.float32).reshape(32, cin).contiguous()
     b_host = None if bias_host is None else bias_host.detach().to("cpu", torch.float32).reshape(32).contiguous()
     Hp = Wp = 0
     if prev is not None:
-        if prev.dtype != torch.float16 or prev.dim() != 5 or prev.shape[:2] != (N, 4) or not prev.is_contiguous():
-            raise ValueError("prev must be a contiguous fp16 C8 map [N,4,Hp,Wp,8]")
-        Hp, Wp = prev.shape[2:4]
-    out = torch.empty((N, 4, H, W, 8), dtype=torch.float16, device=x.device)
+        Np, CBp, Hp, Wp = _map_dims(prev, prev_folded)
+        if prev.dtype != torch.float16 or (Np, CBp) != (N, 4):
+            raise ValueError("prev must be an fp16 C8 map with 32 channels and x's batch")
+    out = torch.empty((4, N, H, W, 8) if out_folded else (N, 4, H, W, 8), dtype=torch.float16, device=x.device)
+    flags = (1 if x_folded else 0) | (2 if out_folded else 0) | (4 if prev_folded else 0)
     with torch.cuda.device(x.device):
-        check(lib().mvs_fpn_merge_c8h(_p(x), _p(w_host), _p(b_host), _p(prev), _p(out), N, cin, H, W, Hp, Wp, _stream()),
+        check(lib().mvs_fpn_merge_c8h(_p(x), _p(w_host), _p(b_host), _p(prev), _p(out), N, cin, H, W, Hp, Wp, flags, _stream()),
               "mvs_fpn_merge_c8h")
     return out

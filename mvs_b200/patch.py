@@ -10,7 +10,7 @@ from __future__ import annotations
 import sys
 import types
 
-from . import modules, ops
+from . import featurenet, modules, ops
 
 _COMMON = {
     "depth_regression": ops.depth_regression,
@@ -22,7 +22,8 @@ _BY_FAMILY = {
                "ConvBnReLU3D": modules.ConvBnReLU3D},
     # CasMVSNet/models/{module,cas_mvsnet}.py
     "cas": {"homo_warping": ops.homo_warping, "CostRegNet": modules.CostRegNetCas, "DepthNet": modules.DepthNet,
-            "Conv3d": modules.Conv3d, "Deconv3d": modules.Deconv3d},
+            "Conv3d": modules.Conv3d, "Deconv3d": modules.Deconv3d, "FeatureNet": featurenet.FeatureNet,
+            "CascadeMVSNet": featurenet.CascadeMVSNet},
     # CVP-MVSNet/models/{modules,net}.py
     "cvp": {"homo_warping": ops.homo_warping_cvp, "proj_cost": modules.proj_cost,
             "depth_regression_refine": ops.depth_regression_refine, "CostRegNet": modules.CostRegNetCVP},

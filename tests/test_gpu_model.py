@@ -100,6 +100,12 @@ def test_s2d_and_fpn_merge_kernels():
     out = ops.fpn_merge_c8h(xc, w, b, ops.pack_c8(prev.float().to(DEV), torch.float16))
     got = out.permute(0, 1, 4, 2, 3).reshape(3, 32, 13, 22).float().cpu()
     np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2 ** -10, atol=1e-3)
+    # folded layouts [CB,N,H,W,8]: same values, block-major order
+    xf = xc.permute(1, 0, 2, 3, 4).contiguous()
+    assert torch.equal(ops.s2d_c8(xf, True, True).permute(1, 0, 2, 3, 4), s) and torch.equal(ops.s2d_c8(xf, True, False), s)
+    pf = ops.pack_c8(prev.float().to(DEV), torch.float16).permute(1, 0, 2, 3, 4).contiguous()
+    of = ops.fpn_merge_c8h(xf, w, b, pf, x_folded=True, out_folded=True, prev_folded=True)
+    assert torch.equal(of.permute(1, 0, 2, 3, 4), out)
     u8 = torch.randint(0, 256, (2, 3, 9, 17), dtype=torch.uint8, generator=g)
     c = ops.img_to_c8h(u8.to(DEV)).cpu()
     assert torch.equal(c[:, 0, :, :, :3].permute(0, 3, 1, 2), (u8.float() / 255.0).half()) and not c[..., 3:].any()

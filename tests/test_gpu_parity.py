@@ -520,6 +520,7 @@ def _both_builders(feats, rot, tr, depth, flags=0):
     trs = [cu(tr[:, i]) for i in range(nsrc)]
     packed = [ops.pack_c8(cu(f), torch.float16) for f in feats]
     d = cu(depth)
+    assert nsrc <= 6, "the TMA builder takes up to 6 source views (more: the library falls back to the gather kernel)"
     tma = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, d, flags | L.WARP_TMA)
     gather = ops.cost_volume_c8(packed[0], packed[1:], rots, trs, d, flags | L.WARP_NO_TMA)
     return tma, gather
@@ -527,7 +528,8 @@ def _both_builders(feats, rot, tr, depth, flags=0):
 
 @pytest.mark.parametrize("C,pixel,nsrc,B,H,W,D", [
     (32, False, 4, 1, 21, 40, 6), (16, True, 4, 2, 37, 50, 12), (8, True, 2, 1, 64, 96, 8), (8, False, 6, 1, 19, 33, 5),
-    (8, True, 1, 1, 8, 32, 3), (16, False, 8, 1, 24, 70, 9), (8, True, 4, 1, 2, 2, 2), (24, True, 3, 2, 130, 161, 17)])
+    (8, True, 1, 1, 8, 32, 3), (16, False, 6, 1, 24, 70, 9), (8, True, 4, 1, 2, 2, 2), (24, True, 3, 2, 130, 161, 17),
+    (8, False, 5, 1, 40, 64, 4), (16, True, 5, 2, 33, 47, 6)])
 def test_tma_builder_equals_gather_builder(C, pixel, nsrc, B, H, W, D):
     """Same taps, same weights, same op order: the staged box only decides WHERE a tap is read from."""
     v, rot, tr = _c8h_case(nsrc + 1, B, C, H, W, D, 70 + C + nsrc, pixel)
