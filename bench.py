@@ -60,6 +60,10 @@ WORKLOADS = {
     "cfg5": dict(kind="cas", key="cfg5", img_hw=(1056, 1920), ndepths=(64, 32, 8),
                  metric="depth-maps/sec (ref-views/sec) at Tanks&Temples 1920x1056, N=7",
                  name="cfg5: CasMVSNet 3-stage 1920x1056 N=7 D=(64,32,8), 4 ref views per GPU per step"),
+    "cfg4": dict(kind="cvp_train", key="cfg4", img_hw=(864, 1152), ndepths=(48, 8), nsrc=4, nscale=2, batch=2,
+                 metric="training samples/sec (ref-views/sec), CVP-MVSNet 1152x864, N=5, nscale=2",
+                 name="cfg4: CVP-MVSNet training step 1152x864 N=5 nscale=2 (D=48 coarse, 8 refine), 2 samples per GPU per step, "
+                      "Adam, single flat NCCL gradient bucket"),
     "cfg2": dict(kind="mvsnet", key="cfg2", img_hw=(512, 640), ndepths=(192,),
                  metric="depth-maps/sec (ref-views/sec) at 640x512, N=5, D=192",
                  name="cfg2: MVSNet 640x512 N=5 D=192, 4 ref views per GPU per step"),
@@ -595,6 +599,163 @@ def parity_and_strict(args, wl, dev, model, build_model, hi, projs, dv, dmin, dm
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# cfg4: CVP-MVSNet training step (BASELINE.json configs[3]) -- the only place the path has a collective
+def cvp_train_inputs(wl, seed, batch, dev):
+    H, W = wl["img_hw"]
+    nsrc = wl["nsrc"]
+    ref_in, src_in, ref_ex, src_ex = [torch.from_numpy(a).to(dev) for a in synth.cvp_cameras(nsrc, W, seed=seed, batch=batch)]
+    imgs = torch.from_numpy(synth.images_u8(nsrc + 1, H, W, seed=seed, batch=batch))
+    dmin = torch.full((batch,), synth.DTU_DEPTH_MIN, dtype=torch.float64, device=dev)
+    dmax = torch.full((batch,), synth.DTU_DEPTH_MAX, dtype=torch.float64, device=dev)
+    gts = [torch.from_numpy(synth.depth_surface(H >> i, W >> i, batch)).to(dev) for i in range(wl["nscale"])]
+    return dict(imgs_u8=imgs, cams=(ref_in, src_in, ref_ex, src_ex), dmin=dmin, dmax=dmax, gts=gts)
+
+
+def main_train(args, wl):
+    import types
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_args = types.SimpleNamespace(nsrc=wl["nsrc"], nscale=wl["nscale"], mode="train")
+    B = wl["batch"]
+    if args.impl == "reference":
+        # the reference's training step on the host cores: forward + backward + Adam through the torch port, ONE sample per step
+        if rank != 0:
+            return
+        from oracle import torch_port as TP
+        from mvs_b200 import pyramid
+        import torch.nn.functional as F
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(SEED_MODEL)
+        sd = {k: v.detach().clone().requires_grad_(v.dtype == torch.float32 and "running" not in k)
+              for k, v in pyramid.network(cfg_args).state_dict().items()}
+        inp = cvp_train_inputs(wl, 0, 1, "cpu")
+        imgs = inp["imgs_u8"].float() / 255.0
+        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-3)
+        times = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            d = TP.cvp_network(imgs[:, 0], imgs[:, 1:], *inp["cams"], inp["dmin"], inp["dmax"], sd, wl["nscale"], True)
+            loss = sum(F.smooth_l1_loss(a[g > 425], g[g > 425], reduction="mean") for a, g in zip(d, inp["gts"]))
+            loss.backward()
+            opt.step()
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        v = len(times) / sum(times)
+        line = {"impl": "reference", "metric": wl["metric"], "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"], "sample_fraction_per_step": 1.0 / B},
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": "1 training sample per step (forward + backward + Adam), oracle/torch_port.py cvp_network, fp32"},
+                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    from mvs_b200 import pyramid, ops, _lib
+    from mvs_b200.train import GradBucket, masked_smooth_l1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    pin_to_gpu_numa(local)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(SEED_MODEL)                       # identical initial weights on every rank (what DDP's broadcast ensures)
+    net = pyramid.network(cfg_args, mode="strict").to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    bucket = GradBucket(net.parameters())
+    inp = cvp_train_inputs(wl, rank, B, dev)
+    host_imgs = inp["imgs_u8"].pin_memory()
+    dimgs = host_imgs.to(dev)
+    host_loss = torch.empty(1).pin_memory()
+
+    def step(imgs_u8):
+        imgs = imgs_u8.float() / 255.0
+        opt.zero_grad(set_to_none=False)
+        out = net(imgs[:, 0], imgs[:, 1:], *inp["cams"], inp["dmin"], inp["dmax"])
+        loss = sum(masked_smooth_l1(d, g, g > 425) for d, g in zip(out["depth_est_list"], inp["gts"]))   # CVP-MVSNet/train.py:205-209
+        loss.backward()
+        bucket.reduce()
+        bucket.wait()
+        opt.step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(dimgs)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ops.KERNEL_TIMERS = {}
+    ms = timed(lambda: step(dimgs), args.steps)
+    timers, ops.KERNEL_TIMERS = ops.KERNEL_TIMERS, None
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+
+    def step_e2e():
+        d = host_imgs.to(dev, non_blocking=True)
+        host_loss.copy_(step(d).reshape(1), non_blocking=True)
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    ev = timers.get("warp_variance", [])
+    kernel_ms = sum(a.elapsed_time(b) for a, b in ev)
+    H, W = wl["img_hw"]
+    per_level = [synth.warp_variance_bytes(wl["nsrc"] + 1, B, 16, d, H >> l, W >> l, 4, 4, per_pixel_depth=(l == 0))
+                 for d, l in zip(wl["ndepths"], (wl["nscale"] - 1, 0))]
+    alg = sum(per_level) * (len(ev) / len(per_level))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    achieved = alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    line = {"metric": wl["metric"], "value": world * B * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "mode": "strict (training always runs the fp32 kernels)", "samples_per_step_per_gpu": B,
+                       "collective": f"one flat bucket of {bucket.numel} fp32 gradients ({bucket.numel * 4 / 1e6:.2f} MB), NCCL all-reduce SUM on a side stream, averaged",
+                       "l2": "activations per step exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(host_imgs.numel()), "d2h_bytes_per_step": 4,
+                    "what": "pinned uint8 images -> H2D -> /255 -> forward + backward + all-reduce + Adam -> D2H loss"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "warp_variance forward (strict fp32 builder, 2 launches/step: coarse planes + per-pixel refine)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg / max(len(ev), 1), "avg_launch_ms": kernel_ms / max(len(ev), 1),
+                         "launches_timed": len(ev), "share_of_step": kernel_ms / ms if ms > 0 else None,
+                         "note": "the strict NCHW builder is the parity kernel (5 % of HBM peak); the training step is dominated by the fp32 "
+                                 "SIMT convolutions (forward, data gradient, weight gradient)"},
+            "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline_note"] = "run `bench.py --config cfg4 --impl reference` for the CPU arm (one training sample per step takes minutes)"
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -610,7 +771,9 @@ if __name__ == "__main__":
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode timing")
     a = ap.parse_args()
     w = WORKLOADS[a.config]
-    if a.impl == "reference":
+    if w["kind"] == "cvp_train":
+        main_train(a, w)
+    elif a.impl == "reference":
         main_reference(a, w)
     else:
         main_ours(a, w)

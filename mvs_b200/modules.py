@@ -94,10 +94,15 @@ def _fold_bn(bn: Optional[nn.BatchNorm3d], cache_owner: nn.Module):
 
 
 def _run_layer(x, weight, bn, stride, transposed, relu, skip, mode, owner):
+    if owner.training and torch.is_grad_enabled():
+        # training step (BASELINE configs[3]): strict fp32 kernels under autograd, batch-statistics BatchNorm (train.py)
+        from . import train
+        if x.dim() != 5:
+            raise L.MvsError("training runs the strict fp32 NCDHW path: build the model with mode='strict'")
+        return train.train_layer(x, weight, bn, stride, transposed, relu, skip)
     if owner.training and bn is not None:
-        raise NotImplementedError(
-            "mvs_b200 CostRegNet: training-mode BatchNorm (batch statistics) is not built yet; "
-            "call .eval() (inference) -- see DESIGN.md 'out of scope this round'")
+        raise L.MvsError("CostRegNet is in training mode but gradients are disabled: call .eval() for inference "
+                         "(train-mode BatchNorm would use and update batch statistics)")
     scale, shift = _fold_bn(bn, owner)
     if mode == "strict":
         return ops.conv3d(x, weight, scale, shift, skip, stride, transposed, relu)
@@ -229,6 +234,10 @@ def _check_divisible(x, k):
 
 
 def _prob_layer(conv: nn.Conv3d, x, mode):
+    if conv.training and torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+        from . import train
+        y = train.Conv3dFn.apply(x, conv.weight, 1, False)
+        return y if conv.bias is None else y + conv.bias.view(1, -1, 1, 1, 1)
     shift = conv.bias.detach().float() if conv.bias is not None else None
     if mode == "strict":
         return ops.conv3d(x, conv.weight, None, shift, None, 1, False, False)
@@ -309,6 +318,9 @@ def _is_fast(cost_regularization) -> bool:
 def regress(cost_reg, depth_values, clamp_index):
     """softmax + depth_regression + photometric confidence on [B,1,D,h,w] or [B,D,h,w] logits."""
     logits = cost_reg.squeeze(1) if cost_reg.dim() == 5 else cost_reg
+    if torch.is_grad_enabled() and logits.requires_grad:
+        from . import train
+        return train.regress_train(logits, depth_values, clamp_index)
     depth, conf, _, _ = ops.softargmin_conf(logits, depth_values, clamp_index=clamp_index)
     return depth, conf
 

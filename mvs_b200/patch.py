@@ -10,7 +10,7 @@ from __future__ import annotations
 import sys
 import types
 
-from . import featurenet, modules, ops
+from . import featurenet, modules, ops, pyramid
 
 _COMMON = {
     "depth_regression": ops.depth_regression,
@@ -26,7 +26,8 @@ _BY_FAMILY = {
             "CascadeMVSNet": featurenet.CascadeMVSNet},
     # CVP-MVSNet/models/{modules,net}.py
     "cvp": {"homo_warping": ops.homo_warping_cvp, "proj_cost": modules.proj_cost,
-            "depth_regression_refine": ops.depth_regression_refine, "CostRegNet": modules.CostRegNetCVP},
+            "depth_regression_refine": ops.depth_regression_refine, "CostRegNet": modules.CostRegNetCVP,
+            "FeaturePyramid": pyramid.FeaturePyramid},
     # MVSNet_pl/models/{modules,mvsnet}.py
     "pl": {"homo_warp": ops.homo_warp},
 }

@@ -132,3 +132,57 @@ def cvp_hot_path(ref_pyramid: Sequence[torch.Tensor], src_pyramids: Sequence[Seq
         depth_list.append(depth)
     depth_list.reverse()
     return {"depth_est_list": depth_list, "prob_confidence": out["photometric_confidence"]}
+
+
+# ---- the caller side: CVP-MVSNet's feature pyramid and the whole `network` (net.py:22-50, 91-207) -----------------------
+def _conv_lrelu(cin, cout):
+    """`conv()` of CVP-MVSNet/models/modules.py:22-26: Conv2d(3x3, bias) + LeakyReLU(0.1); keys ``0.weight, 0.bias``."""
+    return torch.nn.Sequential(torch.nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1, dilation=1, bias=True),
+                               torch.nn.LeakyReLU(0.1))
+
+
+class FeaturePyramid(torch.nn.Module):
+    """CVP-MVSNet/models/net.py:22-50: nine shared 3x3 conv + LeakyReLU layers applied to the image and its bilinear
+    half-resolution copies.  Stays PyTorch (BASELINE north_star: 2D feature extractor)."""
+
+    def __init__(self):
+        super().__init__()
+        chans = [("conv0aa", 3, 64), ("conv0ba", 64, 64), ("conv0bb", 64, 64), ("conv0bc", 64, 32), ("conv0bd", 32, 32),
+                 ("conv0be", 32, 32), ("conv0bf", 32, 16), ("conv0bg", 16, 16), ("conv0bh", 16, 16)]
+        for name, a, b in chans:
+            setattr(self, name, _conv_lrelu(a, b))
+        self._order = [c[0] for c in chans]
+
+    def _net(self, img):
+        f = img
+        for name in self._order:
+            f = getattr(self, name)(f)
+        return f
+
+    def forward(self, img, scales=5):
+        fp = [self._net(img)]
+        for _ in range(scales - 1):
+            img = F.interpolate(img, scale_factor=0.5, mode="bilinear", align_corners=None).detach()
+            fp.append(self._net(img))
+        return fp
+
+
+class network(torch.nn.Module):
+    """Drop-in for CVP-MVSNet/models/net.py:91-207: `network(args)` with args.nsrc / args.nscale / args.mode, the
+    reference's state-dict keys (featurePyramid.*, cost_reg_refine.*), its 8-argument forward and its output dict
+    {"depth_est_list": [finest .. coarsest], "prob_confidence"}.  Training (args.mode == "train", module in .train())
+    runs the strict fp32 kernels under autograd (mvs_b200/train.py)."""
+
+    def __init__(self, args, mode="strict"):
+        super().__init__()
+        from .modules import CostRegNetCVP
+        self.featurePyramid = FeaturePyramid()
+        self.cost_reg_refine = CostRegNetCVP(mode=mode)
+        self.args = args
+
+    def forward(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max):
+        nscale, nsrc = self.args.nscale, self.args.nsrc
+        ref_pyr = self.featurePyramid(ref_img, nscale)
+        src_pyrs = [self.featurePyramid(src_imgs[:, i], nscale) for i in range(nsrc)]
+        return cvp_hot_path(ref_pyr, src_pyrs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max, self.cost_reg_refine,
+                            tuple(ref_img.shape[2:]), mode=getattr(self.args, "mode", "test"))

@@ -191,3 +191,90 @@ def cas_model(imgs, proj_matrices, depth_values, sd, ndepths=(48, 32, 8), ratios
     sds = [{k[len(f"cost_regularization.{i}."):]: v for k, v in sd.items() if k.startswith(f"cost_regularization.{i}.")}
            for i in range(len(ndepths))]
     return cas_cascade(features, proj_matrices, depth_values, sds, ndepths=ndepths, ratios=ratios, img_hw=tuple(imgs.shape[-2:]))
+
+
+# ---- CVP-MVSNet: the whole `network` (feature pyramid + coarse-to-fine hot path), eval or training -------------------
+def _cvp_feature(img, sd, p):
+    """FeaturePyramid's shared nine-layer CNN (CVP-MVSNet/models/net.py:28-43; `conv()` = Conv2d + LeakyReLU(0.1))."""
+    f = img
+    for name in ("conv0aa", "conv0ba", "conv0bb", "conv0bc", "conv0bd", "conv0be", "conv0bf", "conv0bg", "conv0bh"):
+        f = F.leaky_relu(F.conv2d(f, sd[f"{p}{name}.0.weight"], sd[f"{p}{name}.0.bias"], padding=1), 0.1)
+    return f
+
+
+def cvp_feature_pyramid(img, sd, scales, p="featurePyramid."):
+    """net.py:39-50: the image and its bilinear half-resolution copies through the same CNN; finest level first."""
+    fp = [_cvp_feature(img, sd, p)]
+    for _ in range(scales - 1):
+        img = F.interpolate(img, scale_factor=0.5, mode="bilinear", align_corners=None).detach()
+        fp.append(_cvp_feature(img, sd, p))
+    return fp
+
+
+def _cvp_cbr(x, sd, conv, bn, stride, transposed, train):
+    w = sd[conv + ".weight"]
+    y = (F.conv_transpose3d(x, w, None, stride=stride, padding=1, output_padding=stride - 1) if transposed
+         else F.conv3d(x, w, None, stride=stride, padding=1))
+    if train:
+        y = F.batch_norm(y, None, None, sd[bn + ".weight"], sd[bn + ".bias"], True, 0.1, 1e-5)
+    else:
+        y = F.batch_norm(y, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"], sd[bn + ".bias"], False, 0.1, 1e-5)
+    return F.relu(y)
+
+
+def cvp_costreg(x, sd, p="cost_reg_refine.", train=False):
+    """CVP CostRegNet.forward (net.py:78-89), eval or train-mode BatchNorm."""
+    c = lambda t, n, s=1: _cvp_cbr(t, sd, f"{p}{n}.conv", f"{p}{n}.bn", s, False, train)
+    c0 = c(c(x, "conv0"), "conv0a")
+    c2 = c(c(c(c0, "conv1", 2), "conv2"), "conv2a")
+    c4 = c(c(c(c2, "conv3"), "conv4"), "conv4a")
+    c5 = c2 + _cvp_cbr(c4, sd, f"{p}conv5.0", f"{p}conv5.1", 1, True, train)
+    c6 = c0 + _cvp_cbr(c5, sd, f"{p}conv6.0", f"{p}conv6.1", 2, True, train)
+    return F.conv3d(c6, sd[f"{p}prob0.weight"], sd[f"{p}prob0.bias"], padding=1).squeeze(1)
+
+
+def cvp_network(ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max, sd, nscale=2, train=True):
+    """network.forward (net.py:99-207) with args.mode = "train" | "test" semantics for the hypotheses (train: the fixed
+    6.8085 interval of modules.py:134-143).  Returns depth_est_list, finest first.  Out-of-place accumulation (the training
+    branch, net.py:141-143); the aliasing quirk (sum starts from ref**2, net.py:129-130 / modules.py:228-229) is kept."""
+    nsrc = src_imgs.shape[1]
+    B = ref_img.shape[0]
+    ref_p = cvp_feature_pyramid(ref_img, sd, nscale)
+    src_p = [cvp_feature_pyramid(src_imgs[:, i], sd, nscale) for i in range(nsrc)]
+    H = ref_img.shape[2]
+
+    def cond(k, level):                                         # conditionIntrinsics, modules.py:29-50
+        k = k.clone()
+        k[:, :2, :] = k[:, :2, :] / (H / ref_p[level].shape[2])
+        return k
+
+    def proj(k, e):
+        last = torch.tensor([[[0, 0, 0, 1.0]]], device=k.device, dtype=k.dtype).repeat(B, 1, 1)
+        return torch.cat((torch.matmul(k, e[:, 0:3, :]), last), 1)
+
+    def volume(level, hyp):
+        D = hyp.shape[1]
+        r2 = ref_p[level].unsqueeze(2).repeat(1, 1, D, 1, 1) ** 2
+        vs, vq = r2, r2
+        rp = proj(cond(ref_in, level), ref_ex)
+        for i in range(nsrc):
+            w = warp_volume(src_p[i][level], proj(cond(src_in[:, i], level), src_ex[:, i]), rp, hyp)
+            vs = vs + w
+            vq = vq + w ** 2
+        return vq / (nsrc + 1) - (vs / (nsrc + 1)) ** 2
+
+    lo, hi = depth_min[0].double(), depth_max[0].double()
+    planes = (lo + (hi - lo) / 47 * torch.arange(48, dtype=torch.float64, device=ref_img.device)).float().unsqueeze(0).repeat(B, 1)
+    depths = []
+    p = F.softmax(cvp_costreg(volume(nscale - 1, planes), sd, train=train), 1)
+    depth = torch.sum(p * planes.view(B, 48, 1, 1), 1)
+    depths.append(depth)
+    for level in range(nscale - 2, -1, -1):
+        up = F.interpolate(depth[None, :], size=None, scale_factor=2, mode="bicubic", align_corners=None).squeeze(0)
+        assert train, "the test-mode statistical interval of calDepthHypo is not ported (mvs_b200/pyramid.py has it)"
+        hyp = up.unsqueeze(1) + torch.arange(-4, 4, device=up.device, dtype=up.dtype).view(1, 8, 1, 1) * 6.8085
+        p = F.softmax(cvp_costreg(volume(level, hyp), sd, train=train), 1)
+        depth = torch.sum(p * hyp, 1)
+        depths.append(depth)
+    depths.reverse()
+    return depths

@@ -52,3 +52,38 @@ def test_shard_single_process_and_errors():
     with pytest.raises(ValueError):
         D.shard_ref_views(4, 2, 2)
     assert D.max_over_ranks(3.5) == 3.5 and D.gather_counts(4) == [4]
+
+
+def _bucket_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mvs_b200.train import GradBucket
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    list(net.parameters())[1].grad = None                      # a parameter without gradient contributes zeros
+    b = GradBucket(net.parameters())
+    b.reduce(); b.wait()
+    q.put((rank, [float(p.grad.flatten()[0]) for p in net.parameters()], b.numel))
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_world2():
+    """GradBucket (the DDP role of CasMVSNet/train.py:367-372): one flat bucket, SUM all-reduce, mean over ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 431
+    ps = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+    for rank, grads, numel in res:
+        # mean over ranks of (rank+1)*(i+1) = 1.5*(i+1); the grad-less parameter averages (0 + 0) / 2 = 0
+        assert grads == [1.5, 0.0, 4.5, 6.0] and numel == 5 * 3 + 3 + 3 * 2 + 2
