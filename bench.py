@@ -52,6 +52,27 @@ import torch
 
 from mvs_b200 import synth
 
+# Exactly ONE line on the real stdout: everything else that writes to fd 1 from here on (NCCL's version banner comes from C
+# code and ignored NCCL_DEBUG_FILE on the 2-GPU box, library chatter, warnings) is sent to stderr; emit() writes the JSON
+# line to the saved descriptor.
+_REAL_STDOUT = None          # set in __main__ only: importing bench (tests, tools) must not touch the process's descriptors
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 UNIT = "depth-maps/s"
 WORKLOADS = {
     "cfg3": dict(kind="cas", key="cfg3", img_hw=(1184, 1600), ndepths=(48, 32, 8),
@@ -261,7 +282,7 @@ def main_reference(args, wl):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -521,7 +542,7 @@ def main_ours(args, wl):
     if ref_gpu is not None:
         line["ref_gpu_baseline"] = {"unit": UNIT, "what": "reference op sequence (FeatureNet + grid_sample + cuDNN conv3d, oracle/torch_port.py) "
                                     "on the same GPU from images, 1 ref view per step, cudnn.benchmark=True", **ref_gpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -651,7 +672,7 @@ def main_train(args, wl):
                 "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                                  "sample": "1 training sample per step (forward + backward + Adam), oracle/torch_port.py cvp_network, fp32"},
                 "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     from mvs_b200 import pyramid, ops, _lib
@@ -751,7 +772,7 @@ def main_train(args, wl):
             "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline_note"] = "run `bench.py --config cfg4 --impl reference` for the CPU arm (one training sample per step takes minutes)"
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -770,6 +791,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check and the strict-mode timing")
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode timing")
     a = ap.parse_args()
+    _claim_stdout()
     w = WORKLOADS[a.config]
     if w["kind"] == "cvp_train":
         main_train(a, w)

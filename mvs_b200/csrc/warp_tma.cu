@@ -318,6 +318,9 @@ warp_variance_tma_kernel(const uint4 *__restrict__ ref, SrcPtrs srcs, const floa
 
         // the first box of this item has landed: the wait also publishes s_box[par] (written before the arrive)
         mbar_wait_(&s_full[sub & 1], (sub >> 1) & 1);
+        // The mbarrier (arrive = release after the s_box write, wait = acquire) already orders s_box; the CTA barrier makes the
+        // hand-over visible to compute-sanitizer's racecheck as well (it does not model mbarrier ordering of generic stores)
+        __syncthreads();
 
         float q[NSRC][3];
         int bwv[NSRC];
