@@ -211,6 +211,18 @@ int mvs_depth_range_samples(const float *cur, double interval, int ndepth, float
 int mvs_cas_hypotheses(const float *prev_depth, int hp, int wp, int H, int W, int h, int w, int ndepth,
                        double interval, float *out, int B, void *stream);
 
+/* Relative poses of a CasMVSNet projection block in one launch (fast path; replaces ~25 tiny ATen / cuSOLVER launches per
+ * stage: cas_mvsnet.py:30-33 K[:3,:3] @ E[:3,:4], module.py:257-259 src @ inverse(ref)).  proj [n_sets,N,2,4,4] fp32
+ * ([..,0] extrinsic, [..,1,:3,:3] intrinsic) -> rot [n_sets,N-1,9], trans [n_sets,N-1,3]; fp64 inside, rounded once. */
+int mvs_cas_poses(const float *proj, float *rot, float *trans, int n_sets, int N, void *stream);
+
+/* CVP-MVSNet's statistical hypothesis interval (calDepthHypo test branch, CVP-MVSNet/models/modules.py:146-209):
+ * sum over the image of |delta_d| per batch element, float64.  ref_depth [B,H,W] fp32 (the up-sampled depth map);
+ * cams [B,59] doubles = inv(K_ref)[9] | inv(E_ref)[16] | E_src[16] | K_src[9] | (K_ref R_ref) inv(K_src R_src)[9], derived by
+ * the caller with the reference's own torch ops; sum_abs [B] doubles, ZERO on entry (the mean is sum / (H * W)). */
+int mvs_cvp_depth_interval(const float *ref_depth, const double *cams, double *sum_abs, int B, int H, int W,
+                           double pixel_interval, void *stream);
+
 /* ---- f4: geometric-consistency filter of estimated depth maps (the step after the path) ------
  * Replaces reproject_with_depth + check_geometric_consistency (MVSNet/eval.py:138-208, CasMVSNet/test.py:237-294)
  * and the per-reference-view fusion loop of filter_depth (MVSNet/eval.py:240-263).  Depth / confidence maps fp32 [H,W]

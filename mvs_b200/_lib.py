@@ -64,6 +64,8 @@ SIGNATURES = {
     "mvs_geo_consistency": (_i, [_vp] * 9 + [_i, _i, _d, C.c_float, _i, _vp]),
     "mvs_geo_backproject": (_i, [_vp] * 4 + [_i, _i, _vp]),
     "mvs_geo_fuse": (_i, [_vp, _vp, _vp, _i] + [_vp] * 6 + [_i, _i, _d, C.c_float, C.c_float, _i, _vp]),
+    "mvs_cas_poses": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "mvs_cvp_depth_interval": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp]),
     "mvs_cas_hypotheses": (_i, [_vp] + [_i] * 7 + [_d, _vp, _i, _vp]),
 }
 

@@ -40,7 +40,9 @@ def cascade_hot_path(features: Sequence[Dict[str, torch.Tensor]], proj_matrices:
     depth_interval = (depth_max - depth_min) / depth_values.size(1)
     # relative poses of all stages and views in one batched pass (a handful of launches instead of ~50 per stage)
     keys = ["stage%d" % (i + 1) for i in range(len(ndepths))]
-    rot_all, trans_all = cas_relative_poses(torch.stack([proj_matrices[k] for k in keys], 0))   # [S,B,N-1,9|3]
+    reg0 = cost_regularization[0] if isinstance(cost_regularization, (list, tuple, torch.nn.ModuleList)) else cost_regularization
+    fast = getattr(reg0, "mode", "strict") == "fast" and not torch.is_grad_enabled()
+    rot_all, trans_all = cas_relative_poses(torch.stack([proj_matrices[k] for k in keys], 0), fused_kernel=fast)   # [S,B,N-1,9|3]
     outputs = {}
     depth = None
     for stage_idx, nd in enumerate(ndepths):

@@ -46,6 +46,30 @@ def compile_one(src, force, verbose):
     return obj, p.stderr if verbose else ""
 
 
+def build_variant(name, defines, only=("warp_c8.cu",)):
+    """An experiment build of the same C-ABI (kernel ablations, tuning): recompiles `only` with extra -D flags, links it with
+    the regular objects of everything else into mvs_b200/libmvs_b200_<name>.so (select with MVS_B200_LIB)."""
+    build()
+    vdir = os.path.join(OBJ_DIR, name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in sources():
+        if src in only:
+            obj = os.path.join(vdir, src[:-3] + ".o")
+            cmd = [NVCC, *ARCH, *CFLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(HERE, src), "-o", obj]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")
+        else:
+            obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        objs.append(obj)
+    out = os.path.join(PKG, f"libmvs_b200_{name}.so")
+    p = subprocess.run([NVCC, *ARCH, "-shared", "-o", out, *objs, "-cudart", "static", "-Xcompiler", "-fPIC"], capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = sources()
@@ -64,4 +88,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build("--force" in sys.argv, "--verbose" in sys.argv))
+    if "--variant" in sys.argv:          # python -m mvs_b200.csrc.build --variant abl1 MVS_C8_ABLATE=1
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build("--force" in sys.argv, "--verbose" in sys.argv))

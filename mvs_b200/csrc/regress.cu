@@ -173,3 +173,70 @@ extern "C" int mvs_depth_range_samples(const float *cur, double interval, int nd
     depth_range_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cur, half, ndepth, out, plane);
     return check_launch("mvs_depth_range_samples");
 }
+
+// ---- relative poses of a CasMVSNet projection block in ONE launch ---------------------------------------------------
+// proj [n_sets][N][2][4][4] fp32 ([..,0] = extrinsic E, [..,1,:3,:3] = intrinsic K, CasMVSNet/datasets/general_eval.py);
+// per set: fused_v = E_v with [:3,:4] = K_v[:3,:3] @ E_v[:3,:4] (cas_mvsnet.py:30-33), rel_v = fused_v @ inverse(fused_0)
+// (module.py:257-259) -> rot [n_sets][N-1][9], trans [n_sets][N-1][3].  The reference does this with ~25 tiny ATen / cuSOLVER
+// launches per stage in fp32; here one thread per (set, source view) in fp64, rounded once to fp32 (fast path only: the strict
+// path keeps the torch ops so that both sides of a bit-exactness test consume identical rot / trans bits).
+namespace mvs {
+__device__ inline void fuse_proj(const float *p, double f[16])
+{
+    const float *E = p, *K = p + 16;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) {
+            double a = 0.0;
+            for (int k = 0; k < 3; ++k) a += (double)K[r * 4 + k] * (double)E[k * 4 + c];
+            f[r * 4 + c] = a;
+        }
+    for (int c = 0; c < 4; ++c) f[12 + c] = (double)E[12 + c];
+}
+
+__global__ void cas_poses_kernel(const float *__restrict__ proj, float *__restrict__ rot, float *__restrict__ trans, int n_sets, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sets * (N - 1)) return;
+    const int set = i / (N - 1), v = i % (N - 1) + 1;
+    double a[16], s[16], inv[16];
+    fuse_proj(proj + ((size_t)set * N) * 32, a);
+    fuse_proj(proj + ((size_t)set * N + v) * 32, s);
+    // Gauss-Jordan with partial pivoting on [a | I]
+    double m[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 8; ++c) m[r][c] = c < 4 ? a[r * 4 + c] : (c - 4 == r ? 1.0 : 0.0);
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 4; ++r)
+            if (fabs(m[r][col]) > fabs(m[piv][col])) piv = r;
+        for (int c = 0; c < 8; ++c) { const double t = m[col][c]; m[col][c] = m[piv][c]; m[piv][c] = t; }
+        const double d = 1.0 / m[col][col];
+        for (int c = 0; c < 8; ++c) m[col][c] *= d;
+        for (int r = 0; r < 4; ++r) {
+            if (r == col) continue;
+            const double f = m[r][col];
+            for (int c = 0; c < 8; ++c) m[r][c] -= f * m[col][c];
+        }
+    }
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) inv[r * 4 + c] = m[r][c + 4];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += s[r * 4 + k] * inv[k * 4 + c];
+            if (c < 3) rot[(size_t)i * 9 + r * 3 + c] = (float)acc;
+            else trans[(size_t)i * 3 + r] = (float)acc;
+        }
+    }
+}
+}  // namespace mvs
+
+extern "C" int mvs_cas_poses(const float *proj, float *rot, float *trans, int n_sets, int N, void *stream)
+{
+    if (n_sets == 0 || N <= 1) return MVS_OK;
+    MVS_REQUIRE(n_sets > 0 && N >= 2, "need at least one set and two views");
+    MVS_REQUIRE(proj && rot && trans, "null pointer");
+    const int total = n_sets * (N - 1);
+    mvs::cas_poses_kernel<<<mvs::cdiv(total, 64), 64, 0, (cudaStream_t)stream>>>(proj, rot, trans, n_sets, N);
+    return mvs::check_launch("mvs_cas_poses");
+}

@@ -297,10 +297,25 @@ def stage_forward(features, rot, trans, depth_values, cost_regularization, clamp
     return {"depth": depth, "photometric_confidence": conf}
 
 
-def cas_relative_poses(proj_matrices):
+def cas_relative_poses(proj_matrices, fused_kernel=False):
     """[..., N, 2, 4, 4] CasMVSNet projection blocks -> rot [..., N-1, 9], trans [..., N-1, 3] of every
     source view relative to view 0: K[:3,:3] @ E[:3,:4] (cas_mvsnet.py:30-33), src @ inverse(ref)
-    (module.py:257-259), batched over all leading dimensions."""
+    (module.py:257-259), batched over all leading dimensions.  `fused_kernel` (fast path): ONE launch of
+    mvs_cas_poses (fp64 inside) instead of the ~10 ATen / cuSOLVER launches below; the strict path keeps the torch ops
+    so that parity tests feed identical rot / trans bits to both sides."""
+    if fused_kernel and proj_matrices.is_cuda and proj_matrices.dtype == torch.float32:
+        import ctypes as C
+        p = proj_matrices.contiguous()
+        lead, N = p.shape[:-4], p.shape[-4]
+        n_sets = 1
+        for d in lead:
+            n_sets *= d
+        rot = torch.empty((*lead, N - 1, 9), dtype=torch.float32, device=p.device)
+        trans = torch.empty((*lead, N - 1, 3), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            L.check(L.lib().mvs_cas_poses(C.c_void_p(p.data_ptr()), C.c_void_p(rot.data_ptr()), C.c_void_p(trans.data_ptr()),
+                                          n_sets, N, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mvs_cas_poses")
+        return rot, trans
     with torch.no_grad():
         fused = proj_matrices[..., 0, :, :].clone()
         fused[..., :3, :4] = torch.matmul(proj_matrices[..., 1, :3, :3], proj_matrices[..., 0, :3, :4])

@@ -74,6 +74,24 @@ def _mean_depth_interval(ref_depth, ref_k, src_k, ref_e, src_e, pixel_interval=1
     return delta.abs().mean()
 
 
+def mean_depth_interval_device(ref_depths, ref_in, src_in0, ref_ex, src_ex0, pixel_interval=1.0) -> torch.Tensor:
+    """The same scalar per batch element in ONE kernel launch (mvs_cvp_depth_interval, float64 per pixel like the reference)
+    instead of ~40 full-image float64 torch ops and a batched 2x2 inverse per batch element.  Returns [B] float64."""
+    import ctypes as C
+    B, H, W = ref_depths.shape
+    rk, sk, re, se = ref_in.double(), src_in0.double(), ref_ex.double(), src_ex0.double()
+    a = torch.matmul(torch.matmul(rk, re[:, :3, :3]), torch.inverse(torch.matmul(sk, se[:, :3, :3])))
+    cams = torch.cat([torch.inverse(rk).reshape(B, 9), torch.inverse(re).reshape(B, 16), se.reshape(B, 16), sk.reshape(B, 9),
+                      a.reshape(B, 9)], 1).contiguous()
+    depth = ref_depths.float().contiguous()
+    out = torch.zeros(B, dtype=torch.float64, device=depth.device)
+    with torch.cuda.device(depth.device):
+        L.check(L.lib().mvs_cvp_depth_interval(C.c_void_p(depth.data_ptr()), C.c_void_p(cams.data_ptr()), C.c_void_p(out.data_ptr()),
+                                               B, H, W, float(pixel_interval), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "mvs_cvp_depth_interval")
+    return out / float(H * W)
+
+
 def depth_hypos_refine(mode: str, ref_depths, ref_in, src_in, ref_ex, src_ex, d: int = 4) -> torch.Tensor:
     """calDepthHypo (modules.py:122-219): [B,H,W] up-sampled depth -> [B,2d,H,W] per-pixel hypotheses.
     train: fixed 6.8085 interval; test: the per-batch statistical interval above."""
@@ -83,9 +101,12 @@ def depth_hypos_refine(mode: str, ref_depths, ref_in, src_in, ref_ex, src_ex, d:
         interval = torch.full((B, 1, 1, 1), 6.8085, device=ref_depths.device, dtype=ref_depths.dtype)
     else:
         with torch.no_grad():
-            vals = [_mean_depth_interval(ref_depths[b], ref_in[b].double(), src_in[b, 0].double(), ref_ex[b].double(),
-                                         src_ex[b, 0].double()) for b in range(B)]
-            interval = torch.stack(vals).float().view(B, 1, 1, 1)
+            if ref_depths.is_cuda:
+                interval = mean_depth_interval_device(ref_depths, ref_in, src_in[:, 0], ref_ex, src_ex[:, 0]).float().view(B, 1, 1, 1)
+            else:      # CPU callers (golden generation / oracle side): the reference's op sequence in torch float64
+                vals = [_mean_depth_interval(ref_depths[b], ref_in[b].double(), src_in[b, 0].double(), ref_ex[b].double(),
+                                             src_ex[b, 0].double()) for b in range(B)]
+                interval = torch.stack(vals).float().view(B, 1, 1, 1)
     return (ref_depths.unsqueeze(1) + levels * interval).float()
 
 

@@ -579,3 +579,35 @@ def test_tma_builder_full_size_cfg3(stage):
     del tma
     ref_band = O.cost_volume(feats[0], feats[1:], rot, tr, v["depth"], rows=(y0, y1))
     np.testing.assert_allclose(out, ref_band, rtol=2 ** -7, atol=4e-3)
+
+
+def test_cas_poses_kernel_vs_float64_algebra():
+    """mvs_cas_poses (one launch, fp64 inside) against the reference's K @ E, inverse, product sequence evaluated in float64:
+    equal to fp32 rounding; against the fp32 torch sequence the strict path keeps: within a few fp32 ulps."""
+    from mvs_b200 import modules
+    pm = torch.from_numpy(np.stack([cases.synth.cas_proj_matrices(6, w, seed=3, batch=2) for w in (100, 200, 400)])).to(DEV)   # [S,B,N,2,4,4]
+    rot, trans = modules.cas_relative_poses(pm, fused_kernel=True)
+    rot32, trans32 = modules.cas_relative_poses(pm, fused_kernel=False)
+    p = pm.double()
+    fused = p[..., 0, :, :].clone()
+    fused[..., :3, :4] = p[..., 1, :3, :3] @ p[..., 0, :3, :4]
+    prod = fused[..., 1:, :, :] @ torch.linalg.inv(fused[..., 0, :, :]).unsqueeze(-3)
+    assert rot.shape == (3, 2, 5, 9) and trans.shape == (3, 2, 5, 3)
+    np.testing.assert_allclose(npy(rot), prod[..., :3, :3].reshape(3, 2, 5, 9).float().cpu().numpy(), rtol=2e-7, atol=1e-9)
+    np.testing.assert_allclose(npy(trans), prod[..., :3, 3].float().cpu().numpy(), rtol=2e-7, atol=1e-6)
+    np.testing.assert_allclose(npy(rot), npy(rot32), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(npy(trans), npy(trans32), rtol=1e-4, atol=1e-3)
+
+
+def test_cvp_depth_interval_kernel_vs_reference_op_sequence():
+    """calDepthHypo's statistical interval (CVP-MVSNet/models/modules.py:146-209): the one-launch kernel against the
+    reference's float64 torch op sequence (pyramid._mean_depth_interval, itself pinned by the cvp_network golden)."""
+    from mvs_b200 import pyramid
+    B, H, W = 2, 40, 56
+    ref_in, src_in, ref_ex, src_ex = [cu(a) for a in cases.synth.cvp_cameras(2, W, seed=6, batch=B)]
+    depth = cu(cases.synth.depth_surface(H, W, B) + np.random.RandomState(1).uniform(-3, 3, (B, H, W)).astype(np.float32))
+    got = pyramid.mean_depth_interval_device(depth, ref_in, src_in[:, 0], ref_ex, src_ex[:, 0])
+    ref = torch.stack([pyramid._mean_depth_interval(depth[b], ref_in[b].double(), src_in[b, 0].double(), ref_ex[b].double(),
+                                                    src_ex[b, 0].double()) for b in range(B)])
+    assert got.dtype == torch.float64 and got.shape == (B,)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-9)
