@@ -456,6 +456,58 @@ def main_ours(args, wl):
     for _ in range(NBUF + 1):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps, e2e_tail)
+    e2e_forms = {"serial": ms_e2e}
+
+    # Second launch form (Cas configs, graph mode): the model's two phases as two graphs on two streams -- the feature
+    # extractor of step i+1 runs while the hot path of step i does (its low-resolution layers leave most SMs idle); same
+    # kernels, same results, same copies inside the timed region.  The better form is reported (`e2e.form`).
+    if cas and use_graph:
+        ext_stream = torch.cuda.Stream(device=dev)
+        with torch.no_grad():
+            g_ext = [GraphedStep(lambda j=j: model.extract(dbuf[j])) for j in range(NBUF)]
+        g_hot2 = [GraphedStep(lambda j=j: hot_step(g_ext[j].out)) for j in range(NBUF)]
+        ev_ext = [torch.cuda.Event() for _ in range(NBUF)]
+        ev_hot = [torch.cuda.Event() for _ in range(NBUF)]
+        ev_in2 = [torch.cuda.Event() for _ in range(NBUF)]
+        ev_d2h2 = [torch.cuda.Event() for _ in range(NBUF)]
+        counter2 = [0]
+
+        def step_e2e_2s():
+            i = counter2[0]; counter2[0] += 1
+            j = i % NBUF
+            cur = torch.cuda.current_stream()
+            with torch.cuda.stream(copy_stream):
+                if i >= NBUF:
+                    copy_stream.wait_event(ev_ext[j])        # the extractor that last read this image buffer has finished
+                dbuf[j].copy_(host_in[0], non_blocking=True)
+                ev_in2[j].record(copy_stream)
+            with torch.cuda.stream(ext_stream):
+                ext_stream.wait_event(ev_in2[j])
+                if i >= NBUF:
+                    ext_stream.wait_event(ev_hot[j])         # the hot path that last read these feature maps has finished
+                g_ext[j]()
+                ev_ext[j].record(ext_stream)
+            cur.wait_event(ev_ext[j])
+            if i >= NBUF:
+                cur.wait_event(ev_d2h2[j])
+            out = g_hot2[j]()
+            ev_hot[j].record(cur)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(ev_hot[j])
+                host_outs[j][0].copy_(out["depth"], non_blocking=True)
+                host_outs[j][1].copy_(out["photometric_confidence"], non_blocking=True)
+                ev_d2h2[j].record(d2h_stream)
+
+        def e2e_tail_2s():
+            cur = torch.cuda.current_stream()
+            for j in range(NBUF):
+                cur.wait_event(ev_d2h2[j])
+
+        for _ in range(NBUF + 1):
+            step_e2e_2s()
+        e2e_forms["two_stream"] = timed(step_e2e_2s, args.steps, e2e_tail_2s)
+    e2e_form = min(e2e_forms, key=e2e_forms.get)
+    ms_e2e = e2e_forms[e2e_form]
 
     def h2d_only():
         if cas:
@@ -519,7 +571,8 @@ def main_ours(args, wl):
                    "numa_cpus": numa_cpus},
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
-                "h2d_only_ms_per_step": ms_h2d / args.steps,
+                "h2d_only_ms_per_step": ms_h2d / args.steps, "form": e2e_form,
+                "ms_per_step_by_form": {k: v / args.steps for k, v in e2e_forms.items()},
                 "what": ("pinned uint8 images [B,N,3,H,W] -> H2D -> /255 + FeatureNet mirror + hot path -> D2H depth + confidence "
                          "(the reference's model(imgs, proj_matrices, depth_values) boundary)") if cas else
                         "pinned fp16 C8H feature maps -> H2D -> hot path -> D2H depth + confidence (no MVSNet FeatureNet mirror yet)",
