@@ -102,7 +102,7 @@ def host_inputs(wl, seed=0, batch=None):
         projs = {f"stage{i + 1}": synth.cas_proj_matrices(n, W // s, seed, B) for i, s in enumerate((4, 2, 1))}
         return dict(imgs=synth.images_u8(n, H, W, seed, B), projs=projs, depth_values=synth.depth_planes(192, B))
     c, d, h, w = cfg["stages"][0]
-    return dict(feats=synth.features(n, c, h, w, seed, B), projs=synth.proj_matrices(n, w, seed, B),
+    return dict(imgs=synth.images_u8(n, H, W, seed, B), projs=synth.proj_matrices(n, w, seed, B),
                 depth_values=synth.depth_planes(d, B, hi=synth.DTU_DEPTH_MIN + 2.65 * d))
 
 
@@ -110,7 +110,7 @@ def model_state(wl):
     import cases
     if wl["kind"] == "cas":
         return cases.full_model_state(SEED_MODEL)
-    return cases.costreg_state("mvsnet", seed=SEED_MODEL)
+    return cases.mvsnet_model_state(SEED_MODEL)
 
 
 def algorithmic_bytes(wl, mode, batch):
@@ -185,12 +185,11 @@ def _port_inputs(wl, dev, batch=None):
     hi = host_inputs(wl, batch=batch)
     sd = {k: torch.from_numpy(np.asarray(a)).to(dev) for k, a in model_state(wl).items()}
     dv = torch.from_numpy(hi["depth_values"]).to(dev)
+    imgs = torch.from_numpy(hi["imgs"]).to(dev).float() / 255.0              # general_eval.py:81-86
     if wl["kind"] == "cas":
-        imgs = torch.from_numpy(hi["imgs"]).to(dev).float() / 255.0          # general_eval.py:81-86
         projs = {k: torch.from_numpy(a).to(dev) for k, a in hi["projs"].items()}
         return dict(imgs=imgs, projs=projs, dv=dv, sd=sd)
-    feats = [torch.from_numpy(f).to(dev) for f in hi["feats"]]
-    return dict(feats=feats, projs=torch.from_numpy(hi["projs"]).to(dev), dv=dv, sd=sd)
+    return dict(imgs=imgs, projs=torch.from_numpy(hi["projs"]).to(dev), dv=dv, sd=sd)
 
 
 def _port_step(wl, pi, features=None):
@@ -201,9 +200,12 @@ def _port_step(wl, pi, features=None):
                    for i in range(len(wl["ndepths"]))]
             return TP.cas_cascade(features, pi["projs"], pi["dv"], sds, ndepths=wl["ndepths"], img_hw=wl["img_hw"])
         return TP.cas_model(pi["imgs"], pi["projs"], pi["dv"], pi["sd"], ndepths=wl["ndepths"])
+    if features is None:
+        return TP.mvsnet_model(pi["imgs"], pi["projs"], pi["dv"], pi["sd"])
     projs = torch.unbind(pi["projs"], 1)
-    var = TP.variance_volume(pi["feats"][0], pi["feats"][1:], projs[0], projs[1:], pi["dv"])
-    depth, conf = TP.regress(TP.costreg(var, pi["sd"], "mvsnet"), pi["dv"], clamp_index=False)
+    var = TP.variance_volume(features[0], features[1:], projs[0], projs[1:], pi["dv"])
+    csd = {k[len("cost_regularization."):]: v for k, v in pi["sd"].items() if k.startswith("cost_regularization.")}
+    depth, conf = TP.regress(TP.costreg(var, csd, "mvsnet"), pi["dv"], clamp_index=False)
     return {"depth": depth, "photometric_confidence": conf}
 
 
@@ -219,7 +221,7 @@ def run_cpu_port(wl, steps, warmup):
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
-    what = "images -> FeatureNet x N views -> 3-stage cascade" if wl["kind"] == "cas" else "feature maps -> cost volume -> CostRegNet -> regression"
+    what = "images -> FeatureNet x N views -> 3-stage cascade" if wl["kind"] == "cas" else "images -> FeatureNet x N views -> cost volume -> CostRegNet -> regression"
     return {"value": len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": torch.get_num_threads(),
             "sample": f"1 full reference view per step ({what}; full H/W/D/C/N of {wl['key']}), {len(times)} step(s), "
                       f"torch {torch.__version__} CPU, fp32, oracle/torch_port.py"}
@@ -290,6 +292,7 @@ def main_ours(args, wl):
     import torch.distributed as dist
     from mvs_b200 import modules, cascade, ops, _lib
     from mvs_b200.featurenet import CascadeMVSNet
+    from mvs_b200.mvsnet import MVSNet
     from mvs_b200.graph import GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -336,17 +339,17 @@ def main_ours(args, wl):
             m = CascadeMVSNet(ndepths=wl["ndepths"], mode=mode)
             m.load_state_dict(sd, strict=True)
         else:
-            m = modules.CostRegNet(mode=mode)
+            m = MVSNet(mode=mode)
             m.load_state_dict(sd, strict=True)
         return m.to(dev).eval()
 
     model = build_model(args.mode)
+    host_in = [torch.from_numpy(hi["imgs"]).pin_memory()]                                       # uint8 [B,N,3,H,W]
+    imgs_dev = host_in[0].to(dev)
+    with torch.no_grad():
+        feats = model.extract(imgs_dev)                 # hand-off format of the mode: C8H fp16 (fast) / NCHW fp32 (strict)
     if cas:
         projs = {k: torch.from_numpy(a).to(dev) for k, a in hi["projs"].items()}
-        host_in = [torch.from_numpy(hi["imgs"]).pin_memory()]                                   # uint8 [B,N,3,H,W]
-        imgs_dev = host_in[0].to(dev)
-        with torch.no_grad():
-            feats = model.extract(imgs_dev)             # hand-off format of the mode: C8H fp16 (fast) / NCHW fp32 (strict)
 
         def hot_step(fs=feats, m=model):
             with torch.no_grad():
@@ -359,16 +362,14 @@ def main_ours(args, wl):
         out_shape = (B, *wl["img_hw"])
     else:
         projs = torch.from_numpy(hi["projs"]).to(dev)
-        fdt = torch.float16 if args.mode == "fast" else torch.float32
-        fl = [torch.from_numpy(f).to(dev) for f in hi["feats"]]
-        feats = [ops.pack_c8(f, torch.float16) for f in fl] if args.mode == "fast" else fl
-        host_in = [f.cpu().pin_memory() for f in feats]                                          # hand-off: feature maps
-        del fl
 
         def hot_step(fs=feats, m=model):
             with torch.no_grad():
-                return modules.mvsnet_hot_path(list(fs), projs, dv, m)
-        full_step = None
+                return modules.mvsnet_hot_path(list(fs), projs, dv, m.cost_regularization)
+
+        def full_step(im, m=model):
+            with torch.no_grad():
+                return m(im, projs, dv)
         out_shape = (B, *cfg["stages"][0][2:])
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_in)
     d2h_bytes = 2 * int(np.prod(out_shape)) * 4
@@ -397,22 +398,16 @@ def main_ours(args, wl):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- whole model from device-resident images (FeatureNet mirror + hot path) ----
-    from_images = None
     NBUF = 2
-    if cas:
-        dbuf = [torch.empty_like(host_in[0], device=dev) for _ in range(NBUF)]
-        for t in dbuf:
-            t.copy_(host_in[0])
-        g_full = [GraphedStep(lambda j=j: full_step(dbuf[j])) for j in range(NBUF)] if use_graph else None
-        run_full = (lambda j: g_full[j]()) if use_graph else (lambda j: full_step(dbuf[j]))
-        ms_full = timed(lambda: run_full(0), args.steps)
-        from_images = {"value": world * B * args.steps / (ms_full * 1e-3), "unit": UNIT, "ms_per_step": ms_full / args.steps,
-                       "what": "FeatureNet mirror (fp16 channels-last PyTorch/cuDNN, all N views batched, C8H out) + hot path, "
-                               "uint8 images resident in HBM"}
-    else:
-        dbuf = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(NBUF)]
-        g_full = [GraphedStep(lambda j=j: hot_step(dbuf[j])) for j in range(NBUF)] if use_graph else None
-        run_full = (lambda j: g_full[j]()) if use_graph else (lambda j: hot_step(dbuf[j]))
+    dbuf = [torch.empty_like(host_in[0], device=dev) for _ in range(NBUF)]
+    for t in dbuf:
+        t.copy_(host_in[0])
+    g_full = [GraphedStep(lambda j=j: full_step(dbuf[j])) for j in range(NBUF)] if use_graph else None
+    run_full = (lambda j: g_full[j]()) if use_graph else (lambda j: full_step(dbuf[j]))
+    ms_full = timed(lambda: run_full(0), args.steps)
+    from_images = {"value": world * B * args.steps / (ms_full * 1e-3), "unit": UNIT, "ms_per_step": ms_full / args.steps,
+                   "what": "FeatureNet mirror (native fp16 C8 engine: tcgen05 3x3 layers with the images folded onto the row axis, "
+                           "space-to-depth 5x5/s2 layers, fused FPN laterals; all N views batched, C8H out) + hot path, uint8 images resident in HBM"}
 
     # ---- e2e: every step copies ITS inputs from pinned host memory and reads its result back; the copy of step i+1 (copy
     # stream) and the read-back of step i-1 (its own stream; PCIe is full duplex) overlap the compute of step i ----
@@ -430,11 +425,7 @@ def main_ours(args, wl):
         with torch.cuda.stream(copy_stream):
             if i >= NBUF:
                 copy_stream.wait_event(ev_free[j])           # the step that last read this input buffer has finished
-            if cas:
-                dbuf[j].copy_(host_in[0], non_blocking=True)
-            else:
-                for d, h in zip(dbuf[j], host_in):
-                    d.copy_(h, non_blocking=True)
+            dbuf[j].copy_(host_in[0], non_blocking=True)
             ev_in[j].record(copy_stream)
         cur.wait_event(ev_in[j])
         if i >= NBUF:
@@ -458,10 +449,10 @@ def main_ours(args, wl):
     ms_e2e = timed(step_e2e, args.steps, e2e_tail)
     e2e_forms = {"serial": ms_e2e}
 
-    # Second launch form (Cas configs, graph mode): the model's two phases as two graphs on two streams -- the feature
+    # Second launch form (graph mode): the model's two phases as two graphs on two streams -- the feature
     # extractor of step i+1 runs while the hot path of step i does (its low-resolution layers leave most SMs idle); same
     # kernels, same results, same copies inside the timed region.  The better form is reported (`e2e.form`).
-    if cas and use_graph:
+    if use_graph:
         ext_stream = torch.cuda.Stream(device=dev)
         with torch.no_grad():
             g_ext = [GraphedStep(lambda j=j: model.extract(dbuf[j])) for j in range(NBUF)]
@@ -510,11 +501,7 @@ def main_ours(args, wl):
     ms_e2e = e2e_forms[e2e_form]
 
     def h2d_only():
-        if cas:
-            dbuf[0].copy_(host_in[0], non_blocking=True)
-        else:
-            for d, h in zip(dbuf[0], host_in):
-                d.copy_(h, non_blocking=True)
+        dbuf[0].copy_(host_in[0], non_blocking=True)
     h2d_only()
     ms_h2d = timed(h2d_only, args.steps)
 
@@ -573,9 +560,8 @@ def main_ours(args, wl):
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                 "h2d_only_ms_per_step": ms_h2d / args.steps, "form": e2e_form,
                 "ms_per_step_by_form": {k: v / args.steps for k, v in e2e_forms.items()},
-                "what": ("pinned uint8 images [B,N,3,H,W] -> H2D -> /255 + FeatureNet mirror + hot path -> D2H depth + confidence "
-                         "(the reference's model(imgs, proj_matrices, depth_values) boundary)") if cas else
-                        "pinned fp16 C8H feature maps -> H2D -> hot path -> D2H depth + confidence (no MVSNet FeatureNet mirror yet)",
+                "what": "pinned uint8 images [B,N,3,H,W] -> H2D -> /255 + FeatureNet mirror + hot path -> D2H depth + confidence "
+                        "(the reference's model(imgs, proj_matrices, depth_values) boundary)",
                 "note": "input copy of step i+1 and read-back of step i-1 overlap step i on side streams"},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"kernel": f"warp_variance (fused homography warp + variance, {len(per_stage)} launch(es)/step)", "bound": "hbm",
@@ -587,8 +573,7 @@ def main_ours(args, wl):
                      "share_of_step": kernel_ms / ms_eager if ms_eager > 0 else None},
         "clocks": clocks,
     }
-    if from_images is not None:
-        line["from_images"] = from_images
+    line["from_images"] = from_images
     line.update(extras)
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
@@ -619,9 +604,8 @@ def parity_and_strict(args, wl, dev, model, build_model, hi, projs, dv, dmin, dm
                 ref_hot = _port_step(wl, pi, features=feats32)
                 ks = keys
             else:
-                feats32 = pi["feats"]
-                r = _port_step(wl, pi)
-                ref_hot = {"stage1": r}
+                feats32 = [TP.mvsnet_featurenet(pi["imgs"][:, v], pi["sd"]) for v in range(pi["imgs"].shape[1])]
+                ref_hot = {"stage1": _port_step(wl, pi, features=feats32)}
                 ks = ["stage1"]
         strict = model if args.mode == "strict" else build_model("strict")
         fast = model if args.mode == "fast" else build_model("fast")
@@ -631,7 +615,7 @@ def parity_and_strict(args, wl, dev, model, build_model, hi, projs, dv, dmin, dm
                 if cas:
                     return cascade.cascade_hot_path(fs, projs, dv, m.cost_regularization, ndepths=wl["ndepths"], img_hw=wl["img_hw"],
                                                     depth_min=dmin, depth_max=dmax)
-                return {"stage1": modules.mvsnet_hot_path(list(fs), projs, dv, m)}
+                return {"stage1": modules.mvsnet_hot_path(list(fs), projs, dv, m.cost_regularization)}
 
         res = {}
         for name, m in (("strict", strict), ("fast", fast)):
@@ -642,17 +626,20 @@ def parity_and_strict(args, wl, dev, model, build_model, hi, projs, dv, dmin, dm
                          "vs": "reference op sequence (oracle/torch_port.py) on the same GPU, fp32, TF32 off, same fp32 feature maps in; "
                                "final-stage depth at the benchmarked size; errors compound through the cascade",
                          "hot_path": res}
-        if cas:
-            with torch.no_grad():
-                imgs_u8 = torch.from_numpy(hi["imgs"]).to(dev)
-                ref_full = _port_step(wl, pi)
+        with torch.no_grad():
+            imgs_u8 = torch.from_numpy(hi["imgs"]).to(dev)
+            ref_full = _port_step(wl, pi)
+            if cas:
                 full = {name: depth_errors(m(imgs_u8, projs, dv, depth_min=dmin, depth_max=dmax), ref_full, ks)
                         for name, m in (("strict", strict), ("fast", fast))}
-            out["parity"]["from_images"] = full
+            else:
+                full = {name: depth_errors({"stage1": m(imgs_u8, projs, dv)}, {"stage1": ref_full}, ks)
+                        for name, m in (("strict", strict), ("fast", fast))}
+        out["parity"]["from_images"] = full
         # strict-mode step time (hot path, features resident): the "speed at 1e-4" number
         if args.mode == "fast" and not args.no_strict:
             with torch.no_grad():
-                fs = strict.extract(torch.from_numpy(hi["imgs"]).to(dev)) if cas else feats32
+                fs = strict.extract(torch.from_numpy(hi["imgs"]).to(dev))
             for _ in range(2):
                 hot(strict, fs)
             torch.cuda.synchronize()

@@ -20,6 +20,7 @@ _LAZY = {
     "cascade_hot_path": "cascade", "patch_reference": "patch", "graph": "graph", "GraphedStep": "graph",
     "train": "train", "pyramid": "pyramid", "cvp_hot_path": "pyramid", "FeaturePyramid": "pyramid",
     "featurenet": "featurenet", "FeatureNet": "featurenet", "CascadeMVSNet": "featurenet", "io": "io", "read_pfm": "io",
+    "mvsnet": "mvsnet", "MVSNet": "mvsnet",
     "save_pfm": "io", "write_ply": "io", "filter_depth": "fusion",
     "fusion": "fusion", "reproject_with_depth": "fusion", "check_geometric_consistency": "fusion", "fuse_ref_view": "fusion", "backproject": "fusion",
 }

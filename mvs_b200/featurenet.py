@@ -135,13 +135,17 @@ class _NativeLayer:
         self.conv, self.bn, self.relu, self.key = conv, bn, relu, None
 
     def get(self):
-        ts = [self.conv.weight] + ([self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var] if self.bn is not None else [])
+        ts = [self.conv.weight] + ([self.conv.bias] if self.conv.bias is not None else []) + \
+            ([self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var] if self.bn is not None else [])
         key = tuple((t.data_ptr(), t._version) for t in ts)
         if key != self.key:
             w3 = _as_3x3x3(self.conv.weight)
             self.cout, self.cin = w3.shape[0], w3.shape[1]
             self.packed = ops.pack_conv_weights(w3, 1, False, act_f16=True)
             self.scale, self.shift = _bn_affine(self.bn)
+            if self.conv.bias is not None:          # conv bias (no BN on such layers in the reference: it goes into the shift)
+                b = self.conv.bias.detach().float()
+                self.shift = b.contiguous() if self.shift is None else (self.shift + self.scale * b).contiguous()
             self.key = key
         return self
 

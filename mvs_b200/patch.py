@@ -10,7 +10,7 @@ from __future__ import annotations
 import sys
 import types
 
-from . import featurenet, modules, ops, pyramid
+from . import featurenet, modules, mvsnet, ops, pyramid
 
 _COMMON = {
     "depth_regression": ops.depth_regression,
@@ -19,7 +19,7 @@ _COMMON = {
 _BY_FAMILY = {
     # MVSNet/models/{module,mvsnet}.py
     "mvsnet": {"homo_warping": ops.homo_warping, "CostRegNet": modules.CostRegNetMVSNet,
-               "ConvBnReLU3D": modules.ConvBnReLU3D},
+               "ConvBnReLU3D": modules.ConvBnReLU3D, "FeatureNet": mvsnet.FeatureNet, "MVSNet": mvsnet.MVSNet},
     # CasMVSNet/models/{module,cas_mvsnet}.py
     "cas": {"homo_warping": ops.homo_warping, "CostRegNet": modules.CostRegNetCas, "DepthNet": modules.DepthNet,
             "Conv3d": modules.Conv3d, "Deconv3d": modules.Deconv3d, "FeatureNet": featurenet.FeatureNet,

@@ -278,3 +278,26 @@ def cvp_network(ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, de
         depths.append(depth)
     depths.reverse()
     return depths
+
+
+# ---- MVSNet from images (MVSNet/models/mvsnet.py:8-45, 136-194) ----------------------------------------------------------
+def mvsnet_featurenet(x, sd, p="feature."):
+    def cbr(t, n, stride=1, pad=1):
+        y = F.conv2d(t, sd[f"{p}{n}.conv.weight"], None, stride=stride, padding=pad)
+        y = F.batch_norm(y, sd[f"{p}{n}.bn.running_mean"], sd[f"{p}{n}.bn.running_var"], sd[f"{p}{n}.bn.weight"], sd[f"{p}{n}.bn.bias"],
+                         False, 0.1, 1e-5)
+        return F.relu(y, inplace=True)
+    x = cbr(cbr(x, "conv0"), "conv1")
+    x = cbr(cbr(cbr(x, "conv2", 2, 2), "conv3"), "conv4")
+    x = cbr(cbr(x, "conv5", 2, 2), "conv6")
+    return F.conv2d(x, sd[p + "feature.weight"], sd[p + "feature.bias"], padding=1)
+
+
+def mvsnet_model(imgs, proj_matrices, depth_values, sd):
+    """MVSNet.forward, refine=False, eval branch.  imgs [B,N,3,H,W]; proj_matrices [B,N,4,4]; depth_values [B,D]."""
+    feats = [mvsnet_featurenet(imgs[:, v], sd) for v in range(imgs.shape[1])]
+    projs = torch.unbind(proj_matrices, 1)
+    var = variance_volume(feats[0], feats[1:], projs[0], projs[1:], depth_values)
+    csd = {k[len("cost_regularization."):]: v for k, v in sd.items() if k.startswith("cost_regularization.")}
+    depth, conf = regress(costreg(var, csd, "mvsnet"), depth_values, clamp_index=False)
+    return {"depth": depth, "photometric_confidence": conf}

@@ -94,6 +94,31 @@ def featurenet_state(seed: int = 0) -> dict:
     return synth.fill_state_dict(featurenet_shapes(), seed)
 
 
+def mvsnet_featurenet_shapes() -> dict:
+    """MVSNet/models/mvsnet.py:8-45."""
+    s = {}
+    for name, cin, cout, k in (("conv0", 3, 8, 3), ("conv1", 8, 8, 3), ("conv2", 8, 16, 5), ("conv3", 16, 16, 3), ("conv4", 16, 16, 3),
+                               ("conv5", 16, 32, 5), ("conv6", 32, 32, 3)):
+        s[name + ".conv.weight"] = (cout, cin, k, k)
+        for t, shp in (("weight", (cout,)), ("bias", (cout,)), ("running_mean", (cout,)), ("running_var", (cout,)),
+                       ("num_batches_tracked", ())):
+            s[f"{name}.bn.{t}"] = shp
+    s["feature.weight"] = (32, 32, 3, 3)
+    s["feature.bias"] = (32,)
+    return s
+
+
+def mvsnet_model_state(seed: int = 60) -> dict:
+    sd = {"feature." + k: v for k, v in synth.fill_state_dict(mvsnet_featurenet_shapes(), seed).items()}
+    sd.update({"cost_regularization." + k: v for k, v in costreg_state("mvsnet", seed=seed + 1).items()})
+    return sd
+
+
+def mvsnet_model_case(n_views=3, B=2, H=64, W=96, D=8, seed=13):
+    return dict(imgs_u8=synth.images_u8(n_views, H, W, seed, B), proj=synth.proj_matrices(n_views, W // 4, seed, B),
+                depth=synth.depth_planes(D, B))
+
+
 def full_model_case(n_views=3, B=1, H=64, W=96, ndepths=(16, 8, 8), seed=9):
     """Whole CascadeMVSNet from uint8 images (the loader's /255 scaling applied by the caller / on the device)."""
     projs = {f"stage{i + 1}": synth.cas_proj_matrices(n_views, W // s, seed, B) for i, s in enumerate((4, 2, 1))}

@@ -299,7 +299,23 @@ def gen_casfeat():
     save("cas_full_model", **arrays)
 
 
-GEN = {"mvsnet": gen_mvsnet, "cas": gen_cas, "cvp": gen_cvp, "pl": gen_pl, "casfeat": gen_casfeat}
+def gen_mvsnetfeat():
+    """MVSNet's own FeatureNet + the WHOLE MVSNet.forward from images (MVSNet/models/mvsnet.py:8-45,136-194), nothing stubbed."""
+    import torch
+    import cases
+    sys.path.insert(0, os.path.join(REF, "MVSNet"))
+    from models.mvsnet import MVSNet
+    torch.set_grad_enabled(False)
+    k = cases.mvsnet_model_case()
+    model = MVSNet(refine=False).eval()
+    load_sd(model, cases.mvsnet_model_state())
+    imgs = t(k["imgs_u8"]).float() / 255.0
+    feat = model.feature(imgs[:, 1])
+    res = model(imgs, t(k["proj"]), t(k["depth"]))
+    save("mvsnet_full_model", feature_view1=feat.numpy(), depth=res["depth"].numpy(), conf=res["photometric_confidence"].numpy())
+
+
+GEN = {"mvsnet": gen_mvsnet, "cas": gen_cas, "cvp": gen_cvp, "pl": gen_pl, "casfeat": gen_casfeat, "mvsnetfeat": gen_mvsnetfeat}
 
 if __name__ == "__main__":
     if not os.path.isdir(REF):

@@ -189,3 +189,27 @@ def test_full_cfg3_cascade_strict_and_fast_vs_on_device_reference_ops():
     band = O.cost_volume(f1[0].cpu().numpy(), np.stack([f.cpu().numpy() for f in f1[1:]]), rot.cpu().numpy(), trans.cpu().numpy(),
                          planes.cpu().numpy(), rows=(y0, y1))
     assert np.array_equal(var[:, :, :, y0:y1].cpu().numpy(), band)
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_mvsnet_dropin_from_images_vs_reference_golden(mode):
+    """MVSNet model(imgs, proj_matrices, depth_values) from images against the unmodified reference (make_golden.py mvsnetfeat)."""
+    from mvs_b200.mvsnet import MVSNet
+    gold = cases.golden("mvsnet_full_model")
+    k = cases.mvsnet_model_case()
+    model = MVSNet(mode=mode)
+    model.load_state_dict(_sd(cases.mvsnet_model_state()), strict=True)
+    model = model.to(DEV).eval()
+    imgs = cu(k["imgs_u8"]) if mode == "fast" else cu(k["imgs_u8"]).float() / 255.0
+    with torch.no_grad():
+        out = model(imgs, cu(k["proj"]), cu(k["depth"]))
+        f = model.feature(cu(k["imgs_u8"])[:, 1], mode=mode)
+    g = gold["feature_view1"]
+    ferr = np.abs(f.float().cpu().numpy() - g).max() / np.abs(g).max()
+    d, gd = out["depth"].cpu().numpy(), gold["depth"]
+    rel = np.abs(d - gd) / gd
+    print(mode, "feature max err / max", ferr, "depth rel linf", rel.max(), "l1", np.abs(d - gd).mean() / gd.mean())
+    if mode == "strict":
+        assert ferr <= 2e-5 and rel.max() <= 1e-4
+    else:
+        assert ferr <= 1e-2 and np.abs(d - gd).mean() / gd.mean() <= 3e-3

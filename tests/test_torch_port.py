@@ -85,3 +85,21 @@ def test_full_model_port_matches_reference():
     for s in ("stage1", "stage2", "stage3"):
         np.testing.assert_allclose(out[s]["depth"].numpy(), gold[s + "_depth"], rtol=1e-6)
         np.testing.assert_allclose(out[s]["photometric_confidence"].numpy(), gold[s + "_conf"], rtol=1e-5, atol=1e-6)
+
+
+def test_mvsnet_model_port_and_mirror_keys():
+    """Whole MVSNet.forward from images (tests/golden/mvsnet_full_model.npz): the torch port the CPU arm would time, and the
+    mirror's state-dict key set / strict-mode extractor (same ATen sequence: bit-exact)."""
+    from mvs_b200.mvsnet import MVSNet
+    gold = cases.golden("mvsnet_full_model")
+    k = cases.mvsnet_model_case()
+    sd = sdt(cases.mvsnet_model_state())
+    imgs = t(k["imgs_u8"]).float() / 255.0
+    with torch.no_grad():
+        out = TP.mvsnet_model(imgs, t(k["proj"]), t(k["depth"]), sd)
+        m = MVSNet(mode="strict").eval()
+        m.load_state_dict(sd, strict=True)
+        feat = m.feature(t(k["imgs_u8"])[:, 1])                     # uint8 in: normalised like the loader
+    np.testing.assert_allclose(out["depth"].numpy(), gold["depth"], rtol=1e-6)
+    np.testing.assert_allclose(out["photometric_confidence"].numpy(), gold["conf"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(feat.numpy(), gold["feature_view1"])
