@@ -46,6 +46,9 @@ extern "C" {
 #define MVS_FEAT_F16 256        /* C8 builder: feature maps are fp16 C8 (mvs_pack_c8h); blend in packed fp16  */
 #define MVS_WARP_NO_TMA 512     /* C8 builder: force the L1-gather kernel                                       */
 #define MVS_ACT_F16 2048        /* conv3d_c8: activations, packed weights and output are fp16 C8 instead of bf16 C8   */
+#define MVS_X_DW 4096          /* conv3d_c8 (stride 2): x has W de-interleaved, column w at (w&1)*ceil(W/2) + (w>>1)      */
+#define MVS_Y_DW 8192          /* conv3d_c8 (stride 1): write y W-de-interleaved (for a stride-2 consumer / a skip add)    */
+#define MVS_SKIP_DW 16384      /* conv3d_c8: the skip tensor is W-de-interleaved                                            */
 #define MVS_WARP_TMA 1024       /* C8 builder: force the TMA-staged kernel (fp16 maps only); neither bit: library picks */
 
 /* depth_mode */

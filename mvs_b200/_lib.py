@@ -24,6 +24,7 @@ FEAT_F16 = 256
 WARP_NO_TMA = 512
 WARP_TMA = 1024
 ACT_F16 = 2048
+X_DW, Y_DW, SKIP_DW = 4096, 8192, 16384      # conv3d_c8: W-de-interleaved input / output / skip tensor
 DEPTH_PLANE = 0
 DEPTH_PIXEL = 1
 F32 = 0

@@ -102,6 +102,10 @@ struct ConvPlan {
     int n_ops, n_acc, steps;
     int relu, out_f32, has_skip;
     int f16;                  // MVS_ACT_F16: activations / weights / output are fp16 instead of bf16 (same 16-bit C8 layout)
+    // "DW" = W de-interleaved: column w of a row sits at (w & 1) * ceil(W / 2) + (w >> 1), i.e. [even columns | odd columns].
+    // A stride-1 layer writes it (y_dw) so that the stride-2 layer reading it (x_dw) stages its even / odd arrays from
+    // CONTIGUOUS bytes, and the transposed layer adding it as skip (skip_dw) reads one contiguous run per output parity.
+    int x_dw, y_dw, skip_dw;
     int n_issuers, zero_units;                      // zero_units: 16 B units of the all-zero B block (merged mode)
     int merged;                                     // stride-1 kh-merged mode: 2 issuers alternate depth steps, epilogue frees slabs
     // T-merged mode (stride 1): ONE MMA per (input row, k-step) carries all nine (row tap, step tap) weights along N,
@@ -184,6 +188,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // x / ring and x % ring without a hardware-less integer division (~25 dependent instructions each): exact for x < 32768
 __device__ __forceinline__ int div_ring(int x, uint32_t magic) { return (int)(((uint32_t)x * magic) >> 18); }
 __device__ __forceinline__ int mod_ring(int x, int ring, uint32_t magic) { return x - div_ring(x, magic) * ring; }
+
+// position of column w in a W-de-interleaved row (we = ceil(W / 2))
+__device__ __forceinline__ int dw_col(int w, int we) { return (w & 1) * we + (w >> 1); }
 
 struct RoleTimer {          // accumulates in registers (a global read-modify-write per lap would cost ~700 clk each)
     long long *p; long long t, a0, a1, a2;
@@ -337,7 +344,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int oh = P.oh_mul * (h0 + ao.th) + ao.dh, od0 = P.od_mul * step_begin + ao.dd;
         const size_t plane_o = (size_t)P.Hor * P.Wo;
         const size_t off = P.swap ? (size_t)oh * plane_o + (size_t)od0 * P.Wo : (size_t)od0 * plane_o + (size_t)oh * P.Wo;
-        s_acc[tid] = make_ulonglong2((unsigned long long)(uint32_t)(off + (size_t)ao.wadd),
+        // high half of x: the same voxel's offset in a W-de-interleaved skip tensor, less the thread's column / 2
+        // (transposed layers only: ow = 2 (m0 + m) + wadd sits at (wadd & 1) * ceil(Wo / 2) + m0 + m)
+        const unsigned long long off_dw = (unsigned long long)(uint32_t)(off + (size_t)((ao.wadd & 1) * ((P.Wo + 1) >> 1)));
+        s_acc[tid] = make_ulonglong2((unsigned long long)(uint32_t)(off + (size_t)ao.wadd) | (off_dw << 32),
                                      (unsigned long long)((uint32_t)ao.dd | ((uint32_t)ao.wadd << 8) | ((oh < P.Ho ? 1u : 0u) << 16)));
     }
     if (!TM) {
@@ -377,13 +387,15 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         // output index of (row a, step): pos0 + a * row_stride + step * step_stride  (hoisted 64-bit arithmetic)
         const size_t plane_o = (size_t)P.Hor * P.Wo;
         const size_t row_stride = P.swap ? plane_o : (size_t)P.Wo, step_stride = P.swap ? (size_t)P.Wo : plane_o;
-        const size_t pos0 = (size_t)h0 * row_stride + (size_t)step_begin * step_stride + (size_t)ow;
+        const size_t pos00 = (size_t)h0 * row_stride + (size_t)step_begin * step_stride;
+        const size_t pos0 = pos00 + (size_t)ow;
         const bool w_ok = ow < P.Wo;
         const size_t chunk_base = ((size_t)b * P.cout_chunks + (size_t)ct * nb) * vol_o;
+        const int we_o = (P.Wo + 1) >> 1;
         // 64-bit bases once per thread, 32-bit offsets in the loops (ptxas re-materialised the 64-bit index arithmetic per
         // row otherwise: ~50 of the ~140 instructions a row cost).  The launcher checks that the offsets fit 32 bits.
-        uint4 *const ybase = reinterpret_cast<uint4 *>(y) + chunk_base + pos0;
-        const uint4 *const sbase = skip + chunk_base + pos0;
+        uint4 *const ybase = reinterpret_cast<uint4 *>(y) + chunk_base + pos00 + (size_t)(P.y_dw ? dw_col(ow, we_o) : ow);
+        const uint4 *const sbase = skip + chunk_base + pos00 + (size_t)(P.skip_dw ? dw_col(ow, we_o) : ow);
         float *const fbase = reinterpret_cast<float *>(y) + (size_t)b * vol_o + pos0;
         const uint32_t rs32 = (uint32_t)row_stride, ss32 = (uint32_t)step_stride, vo32 = (uint32_t)vol_o;
         // folded-BN affine of the first 8-channel block in registers (the only block when Cout <= 8)
@@ -508,7 +520,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 #pragma unroll
             for (int cc = 0; cc < (UM_COLS + 31) / 32; ++cc) {
                 const int w_in = P.w_step * (cc * 32 + lane) + P.w_step * m0 + P.w_base[a];
-                wofs[a][cc] = (w_in >= 0 && w_in < P.W) ? w_in : -1;
+                wofs[a][cc] = (w_in >= 0 && w_in < P.W) ? (P.x_dw ? dw_col(w_in, (P.W + 1) >> 1) : w_in) : -1;
             }
         const size_t slab_stride = P.swap ? (size_t)P.W : plane_in;
         if (TM) {
@@ -822,11 +834,15 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             };
             const int od_step = P.od_mul * (step_begin + step);                   // + dd = output position on the step axis
             const uint32_t step_off = (uint32_t)step * epi_step_stride + (uint32_t)ow_thread;
-            auto out_pos = [&](int a, bool &ok) -> uint32_t {    // voxel offset of accumulator a's row for this thread
+            // voxel offset of accumulator a's row for this thread in y (return value) and in the skip tensor (spos)
+            const uint32_t step_off_dw = (uint32_t)step * epi_step_stride + (uint32_t)(ow_thread >> 1);
+            auto out_pos = [&](int a, bool &ok, uint32_t &spos) -> uint32_t {
                 const ulonglong2 e = s_acc[a];
                 const uint32_t f = (uint32_t)e.y;
                 ok = (f >> 16) != 0 && od_step + (int)(f & 0xffu) < P.Do && ow_thread + (int)((f >> 8) & 0xffu) < P.Wo;
-                return (uint32_t)e.x + step_off;
+                const uint32_t pos = (uint32_t)e.x + step_off;
+                spos = P.skip_dw ? (uint32_t)(e.x >> 32) + step_off_dw : pos;
+                return pos;
             };
             if (P.out_f32) {
                 // `prob` layer: one real channel -> fp32 logits; four rows' single-column loads per wait
@@ -840,7 +856,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     for (int j = 0; j < 4; ++j) {
                         if (a0 + j >= P.n_acc) break;
                         bool ok;
-                        const uint32_t pos = out_pos(a0 + j, ok);
+                        uint32_t spos;
+                        const uint32_t pos = out_pos(a0 + j, ok, spos);
                         if (!ok) continue;
                         float o = fmaf(__uint_as_float(r[j]), sc2[0].x, sh2[0].x);
                         if (P.relu) o = fmaxf(o, 0.f);
@@ -853,7 +870,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 constexpr int EB = MC >= 3 ? 2 : 4;
                 for (int a0 = EB * eg; a0 < P.n_acc; a0 += EB * NEG) {
                     uint32_t r[EB][8];
-                    uint32_t pos[EB];
+                    uint32_t pos[EB], spos[EB];
                     bool ok[EB];
                     uint4 sk[EB];
 #pragma unroll
@@ -861,8 +878,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         ok[j] = false;
                         sk[j] = make_uint4(0, 0, 0, 0);
                         if (a0 + j < P.n_acc) {
-                            pos[j] = out_pos(a0 + j, ok[j]);
-                            if (kSkip && ok[j]) sk[j] = __ldg(sbase + pos[j]);
+                            pos[j] = out_pos(a0 + j, ok[j], spos[j]);
+                            if (kSkip && ok[j]) sk[j] = __ldg(sbase + spos[j]);
                             tmem_ld8_nowait(tcol0 + (uint32_t)((a0 + j) * P.n), r[j]);
                         }
                     }
@@ -874,7 +891,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             } else {
                 for (int a = eg; a < P.n_acc; a += NEG) {
                     bool ok;
-                    const uint32_t pos = out_pos(a, ok);
+                    uint32_t spos;
+                    const uint32_t pos = out_pos(a, ok, spos);
                     for (int n0 = 0; n0 < P.n; n0 += 16) {
                         uint32_t r[16];
                         const int c0 = ct * P.n + n0;
@@ -882,8 +900,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         const uint32_t base = (uint32_t)(n0 >> 3) * vo32 + pos;
                         uint4 sk_lo = make_uint4(0, 0, 0, 0), sk_hi = make_uint4(0, 0, 0, 0);
                         if (kSkip && live) {
-                            sk_lo = __ldg(sbase + base);
-                            if (has_hi) sk_hi = __ldg(sbase + base + vo32);
+                            const uint32_t sb = (uint32_t)(n0 >> 3) * vo32 + spos;
+                            sk_lo = __ldg(sbase + sb);
+                            if (has_hi) sk_hi = __ldg(sbase + sb + vo32);
                         }
                         tmem_ld16_nowait(tcol0 + (uint32_t)(a * P.n + n0), r);
                         tmem_wait_ld();
@@ -1377,6 +1396,11 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     if (!build_plan(P, g, B, Cin, Cout, Di, Hi, W, stride, transposed, flags, out_f32, skip_c8 != nullptr, smem))
         return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_fwd: no tile configuration fits shared memory / TMEM for this layer");
     MVS_REQUIRE(!(out_f32 && skip_c8), "skip is not supported on the fp32 (Cout == 1) output");
+    P.x_dw = (flags & MVS_X_DW) ? 1 : 0; P.y_dw = (flags & MVS_Y_DW) ? 1 : 0; P.skip_dw = (flags & MVS_SKIP_DW) ? 1 : 0;
+    MVS_REQUIRE(!P.x_dw || !P.tmerged, "MVS_X_DW: only the stride-2 / transposed layers read a W-de-interleaved input");
+    MVS_REQUIRE(!P.y_dw || (P.tmerged && !out_f32), "MVS_Y_DW: only the stride-1 C8 layers write a W-de-interleaved output");
+    MVS_REQUIRE(!P.skip_dw || skip_c8, "MVS_SKIP_DW without a skip tensor");
+    MVS_REQUIRE(!P.skip_dw || P.tmerged || g.mode == UM_DECONV_S2, "MVS_SKIP_DW: stride-1 and transposed stride-2 layers only");
     P.trace = g_trace; P.trace_ctas = g_trace_ctas;
     P.ring_magic = (1u << 18) / (uint32_t)P.ring + 1u;
     MVS_REQUIRE((long long)P.Do * P.Ho * P.Wo * (P.n >> 3 > 0 ? P.n >> 3 : 1) < (1ll << 31), "output volume too large for 32-bit tile offsets");

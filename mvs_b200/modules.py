@@ -34,8 +34,8 @@ class ConvBnReLU3D(nn.Module):
         self.bn = nn.BatchNorm3d(out_channels)
         self.stride, self.transposed = stride, False
 
-    def forward(self, x, skip=None, mode="strict"):
-        return _run_layer(x, self.conv.weight, self.bn, self.stride, False, True, skip, mode, self)
+    def forward(self, x, skip=None, mode="strict", layout=0):
+        return _run_layer(x, self.conv.weight, self.bn, self.stride, False, True, skip, mode, self, layout)
 
 
 class Conv3d(nn.Module):
@@ -49,8 +49,8 @@ class Conv3d(nn.Module):
         self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum)
         self.stride, self.relu = stride, relu
 
-    def forward(self, x, skip=None, mode="strict"):
-        return _run_layer(x, self.conv.weight, self.bn, self.stride, False, self.relu, skip, mode, self)
+    def forward(self, x, skip=None, mode="strict", layout=0):
+        return _run_layer(x, self.conv.weight, self.bn, self.stride, False, self.relu, skip, mode, self, layout)
 
 
 class Deconv3d(nn.Module):
@@ -66,8 +66,8 @@ class Deconv3d(nn.Module):
         self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum)
         self.stride, self.relu = stride, relu
 
-    def forward(self, x, skip=None, mode="strict"):
-        return _run_layer(x, self.conv.weight, self.bn, self.stride, True, self.relu, skip, mode, self)
+    def forward(self, x, skip=None, mode="strict", layout=0):
+        return _run_layer(x, self.conv.weight, self.bn, self.stride, True, self.relu, skip, mode, self, layout)
 
 
 def _deconv_seq(cin, cout, stride):
@@ -93,7 +93,8 @@ def _fold_bn(bn: Optional[nn.BatchNorm3d], cache_owner: nn.Module):
     return scale, shift
 
 
-def _run_layer(x, weight, bn, stride, transposed, relu, skip, mode, owner):
+def _run_layer(x, weight, bn, stride, transposed, relu, skip, mode, owner, layout=0):
+    """One conv + BN + ReLU (+ skip) block.  `layout` (fast mode only): L.X_DW / L.Y_DW / L.SKIP_DW of ops.conv3d_c8."""
     if owner.training and torch.is_grad_enabled():
         # training step (BASELINE configs[3]): strict fp32 kernels under autograd, batch-statistics BatchNorm (train.py)
         from . import train
@@ -110,7 +111,7 @@ def _run_layer(x, weight, bn, stride, transposed, relu, skip, mode, owner):
         cin = weight.shape[0] if transposed else weight.shape[1]
         cout = weight.shape[1] if transposed else weight.shape[0]
         return ops.conv3d_c8(x, _packed(weight, stride, transposed, owner), cin, cout, scale, shift, skip, stride,
-                             transposed, relu)
+                             transposed, relu, layout=layout)
     raise L.MvsError(f"unknown CostRegNet mode {mode!r} (use 'strict' or 'fast')")
 
 
@@ -124,8 +125,15 @@ def _packed(weight, stride, transposed, owner):
     return cached[1]
 
 
-def _seq_layer(seq: nn.Sequential, x, skip, mode):
-    return _run_layer(x, seq[0].weight, seq[1], seq[0].stride[0], True, True, skip, mode, seq)
+def _seq_layer(seq: nn.Sequential, x, skip, mode, layout=0):
+    return _run_layer(x, seq[0].weight, seq[1], seq[0].stride[0], True, True, skip, mode, seq, layout)
+
+
+def _dw_flags(mode):
+    """Fast mode: the skip tensors (conv0/2/4) are written W-de-interleaved -- their only readers are the stride-2 layer
+    below (even / odd staged arrays become contiguous runs) and the transposed layer that adds them (one run per output
+    parity).  (y, x, skip) flags; strict mode keeps plain NCDHW."""
+    return (L.Y_DW, L.X_DW, L.SKIP_DW) if mode == "fast" else (0, 0, 0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -153,13 +161,14 @@ class CostRegNetMVSNet(nn.Module):
     def forward(self, x):
         m = self.mode
         _check_divisible(x, 8)
-        conv0 = self.conv0(x, mode=m)
-        conv2 = self.conv2(self.conv1(conv0, mode=m), mode=m)
-        conv4 = self.conv4(self.conv3(conv2, mode=m), mode=m)
-        x = self.conv6(self.conv5(conv4, mode=m), mode=m)
-        x = _seq_layer(self.conv7, x, conv4, m)
-        x = _seq_layer(self.conv9, x, conv2, m)
-        x = _seq_layer(self.conv11, x, conv0, m)
+        yd, xd, sd = _dw_flags(m)
+        conv0 = self.conv0(x, mode=m, layout=yd)
+        conv2 = self.conv2(self.conv1(conv0, mode=m, layout=xd), mode=m, layout=yd)
+        conv4 = self.conv4(self.conv3(conv2, mode=m, layout=xd), mode=m, layout=yd)
+        x = self.conv6(self.conv5(conv4, mode=m, layout=xd), mode=m)
+        x = _seq_layer(self.conv7, x, conv4, m, sd)
+        x = _seq_layer(self.conv9, x, conv2, m, sd)
+        x = _seq_layer(self.conv11, x, conv0, m, sd)
         return _prob_layer(self.prob, x, m)
 
 
@@ -186,13 +195,14 @@ class CostRegNetCas(nn.Module):
     def forward(self, x):
         m = self.mode
         _check_divisible(x, 8)
-        conv0 = self.conv0(x, mode=m)
-        conv2 = self.conv2(self.conv1(conv0, mode=m), mode=m)
-        conv4 = self.conv4(self.conv3(conv2, mode=m), mode=m)
-        x = self.conv6(self.conv5(conv4, mode=m), mode=m)
-        x = self.conv7(x, skip=conv4, mode=m)
-        x = self.conv9(x, skip=conv2, mode=m)
-        x = self.conv11(x, skip=conv0, mode=m)
+        yd, xd, sd = _dw_flags(m)
+        conv0 = self.conv0(x, mode=m, layout=yd)
+        conv2 = self.conv2(self.conv1(conv0, mode=m, layout=xd), mode=m, layout=yd)
+        conv4 = self.conv4(self.conv3(conv2, mode=m, layout=xd), mode=m, layout=yd)
+        x = self.conv6(self.conv5(conv4, mode=m, layout=xd), mode=m)
+        x = self.conv7(x, skip=conv4, mode=m, layout=sd)
+        x = self.conv9(x, skip=conv2, mode=m, layout=sd)
+        x = self.conv11(x, skip=conv0, mode=m, layout=sd)
         return _prob_layer(self.prob, x, m)
 
 
@@ -218,11 +228,12 @@ class CostRegNetCVP(nn.Module):
     def forward(self, x):
         m = self.mode
         _check_divisible(x, 2)
-        conv0 = self.conv0a(self.conv0(x, mode=m), mode=m)
-        conv2 = self.conv2a(self.conv2(self.conv1(conv0, mode=m), mode=m), mode=m)
+        yd, xd, sd = _dw_flags(m)
+        conv0 = self.conv0a(self.conv0(x, mode=m), mode=m, layout=yd)
+        conv2 = self.conv2a(self.conv2(self.conv1(conv0, mode=m, layout=xd), mode=m), mode=m)
         conv4 = self.conv4a(self.conv4(self.conv3(conv2, mode=m), mode=m), mode=m)
         conv5 = _seq_layer(self.conv5, conv4, conv2, m)
-        conv6 = _seq_layer(self.conv6, conv5, conv0, m)
+        conv6 = _seq_layer(self.conv6, conv5, conv0, m, sd)
         return _prob_layer(self.prob0, conv6, m).squeeze(1)
 
 

@@ -451,9 +451,11 @@ def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = 
 
 
 def conv3d_c8(x_c8, packed_w, cin: int, cout: int, scale=None, shift=None, skip_c8=None, stride=1, transposed=False,
-              relu=False, act_f16=False):
+              relu=False, act_f16=False, layout=0):
     """y = [skip +] act(conv(x, w) * scale + shift) on C8 bf16 activations [B,CB,D,H,W,8] (act_f16: fp16 activations,
     weights packed with act_f16 -- the 2D feature extractor runs on this with D = 1).
+    layout: OR of L.X_DW / L.Y_DW / L.SKIP_DW -- the input / output / skip tensor keeps W de-interleaved (column w at
+    (w & 1) * ceil(W / 2) + (w >> 1)); CostRegNet's fast path writes conv0/2/4 that way for their stride-2 consumers.
     Returns C8 [B,ceil(Cout/8),Do,Ho,Wo,8] in the activation dtype, or fp32 [B,1,Do,Ho,Wo] when Cout == 1 (`prob`)."""
     _dev(x_c8, packed_w, scale, shift, skip_c8)
     adt = torch.float16 if act_f16 else torch.bfloat16
@@ -476,7 +478,8 @@ def conv3d_c8(x_c8, packed_w, cin: int, cout: int, scale=None, shift=None, skip_
         raise ValueError("skip_c8 must be a contiguous C8 tensor of the output's shape and dtype")
     with torch.cuda.device(x_c8.device):
         check(lib().mvs_conv3d_c8_fwd(_p(x_c8), _p(packed_w), _p(scale), _p(shift), _p(skip_c8), _p(y), B, cin, cout, D,
-                                      H, W, stride, int(transposed), (L.RELU if relu else 0) | (L.ACT_F16 if act_f16 else 0),
+                                      H, W, stride, int(transposed),
+                                      (L.RELU if relu else 0) | (L.ACT_F16 if act_f16 else 0) | int(layout),
                                       _stream()), "mvs_conv3d_c8_fwd")
     return y
 

@@ -80,6 +80,70 @@ def test_conv3d_c8_layer(cin, cout, stride, transposed, dhw):
         np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=4e-3)
 
 
+def _dw_perm(W):
+    """index list p with natural[..., w] == dw[..., p[w]]: column w sits at (w & 1) * ceil(W / 2) + (w >> 1)."""
+    w = torch.arange(W)
+    return ((w & 1) * ((W + 1) // 2) + (w >> 1)).to(DEV)
+
+
+DW_LAYERS = [
+    # which, cin, cout, stride, transposed, (D, H, W)
+    ("y", 8, 8, 1, False, (3, 5, 41)),       # stride-1 layer writes DW (odd W: ceil(W/2) even columns)
+    ("y", 32, 16, 1, False, (4, 9, 150)),    # two channel blocks, W > 128
+    ("x", 8, 16, 2, False, (5, 7, 61)),      # stride-2 layer reads DW, odd extents
+    ("x", 16, 32, 2, False, (4, 6, 300)),    # two M tiles after striding
+    ("x", 32, 64, 2, False, (4, 8, 50)),     # two Cout tiles
+    ("skip", 16, 8, 2, True, (3, 4, 130)),   # transposed layer adds a DW skip: Cout <= 8 epilogue
+    ("skip", 64, 32, 2, True, (2, 3, 25)),   # ... Cout > 8 epilogue (two blocks per TMEM load)
+]
+
+
+@pytest.mark.parametrize("which,cin,cout,stride,transposed,dhw", DW_LAYERS)
+def test_conv3d_c8_dw_layout(which, cin, cout, stride, transposed, dhw):
+    """MVS_X_DW / MVS_Y_DW / MVS_SKIP_DW: the W-de-interleaved tensors are the natural ones permuted -- the layer's results
+    must be bit-identical to the unflagged run (same MMAs, same epilogue arithmetic, different addresses)."""
+    from mvs_b200 import ops, _lib as L
+    rng = np.random.RandomState(17 + cin + cout)
+    D, H, W = dhw
+    x = ops.pack_c8(cu(bf(rng.standard_normal((2, cin, D, H, W)).astype(np.float32))))
+    wshape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+    packed = ops.pack_conv_weights(cu(bf((rng.standard_normal(wshape) / np.sqrt(27 * cin)).astype(np.float32))), stride, transposed)
+    scale, shift = cu(rng.uniform(0.5, 1.5, cout).astype(np.float32)), cu((0.3 * rng.standard_normal(cout)).astype(np.float32))
+    Wo = 2 * W if transposed else ((W - 1) // 2 + 1 if stride == 2 else W)
+    skip = None
+    if which == "skip":
+        Do, Ho = 2 * D, 2 * H
+        skip = ops.pack_c8(cu(bf(rng.standard_normal((2, cout, Do, Ho, Wo)).astype(np.float32))))
+    ref = ops.conv3d_c8(x, packed, cin, cout, scale, shift, skip, stride, transposed, True)
+    if which == "y":
+        out = ops.conv3d_c8(x, packed, cin, cout, scale, shift, None, stride, transposed, True, layout=L.Y_DW)
+        out = out.index_select(4, _dw_perm(Wo))                      # natural[w] = dw[p[w]]
+    elif which == "x":
+        x_dw = torch.empty_like(x)
+        x_dw.index_copy_(4, _dw_perm(W), x)                          # dw[p[w]] = natural[w]
+        out = ops.conv3d_c8(x_dw.contiguous(), packed, cin, cout, scale, shift, None, stride, transposed, True, layout=L.X_DW)
+    else:
+        s_dw = torch.empty_like(skip)
+        s_dw.index_copy_(4, _dw_perm(Wo), skip)
+        out = ops.conv3d_c8(x, packed, cin, cout, scale, shift, s_dw.contiguous(), stride, transposed, True, layout=L.SKIP_DW)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+
+
+def test_conv3d_c8_dw_flag_validation():
+    from mvs_b200 import ops, _lib as L
+    x = torch.zeros(1, 1, 2, 4, 16, 8, dtype=torch.bfloat16, device=DEV)
+    w1 = ops.pack_conv_weights(torch.zeros(8, 8, 3, 3, 3, device=DEV), 1, False)
+    w2 = ops.pack_conv_weights(torch.zeros(16, 8, 3, 3, 3, device=DEV), 2, False)
+    with pytest.raises(L.MvsError):
+        ops.conv3d_c8(x, w1, 8, 8, layout=L.X_DW)                    # stride-1 layers read natural order only
+    with pytest.raises(L.MvsError):
+        ops.conv3d_c8(x, w2, 8, 16, stride=2, layout=L.Y_DW)         # stride-2 layers write natural order only
+    with pytest.raises(L.MvsError):
+        ops.conv3d_c8(x, w1, 8, 8, layout=L.SKIP_DW)                 # no skip tensor
+
+
 @pytest.mark.parametrize("family,cin", [("mvsnet", 32), ("cas", 16), ("cas", 8), ("cvp", 16)])
 def test_costreg_fast_vs_strict(family, cin):
     """Whole CostRegNet on the tensor-core path vs the strict fp32 path (same weights)."""
