@@ -88,8 +88,14 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    if "--variant" in sys.argv:          # python -m mvs_b200.csrc.build --variant abl1 MVS_C8_ABLATE=1
-        i = sys.argv.index("--variant")
-        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    if "--variant" in sys.argv:          # python -m mvs_b200.csrc.build --variant abl1 MVS_C8_ABLATE=1 [--only conv3d_umma.cu]
+        argv = list(sys.argv)
+        only = ("warp_c8.cu",)
+        if "--only" in argv:
+            j = argv.index("--only")
+            only = tuple(argv[j + 1].split(","))
+            del argv[j:j + 2]
+        i = argv.index("--variant")
+        print(build_variant(argv[i + 1], argv[i + 2:], only))
     else:
         print(build("--force" in sys.argv, "--verbose" in sys.argv))

@@ -523,6 +523,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 wofs[a][cc] = (w_in >= 0 && w_in < P.W) ? (P.x_dw ? dw_col(w_in, (P.W + 1) >> 1) : w_in) : -1;
             }
         const size_t slab_stride = P.swap ? (size_t)P.W : plane_in;
+        // (Stride-2 layers over a W-de-interleaved input, x_dw: their cp.async lanes read contiguous 16 B vectors, 4 L1
+        // wavefronts per instruction instead of 8.  One bulk copy per staged line was tried on top of that and is not
+        // faster -- conv1 unchanged, the multi-chunk conv3 / conv5 10-25 % slower: 2-3 UBLKCP per lane and slab.)
         if (TM) {
             // A staged line (one row of one channel block, 132 consecutive voxels) is contiguous in global memory, so it
             // moves as ONE bulk copy issued by one lane (lane l of producer warp p owns line p + 4 l); only the out-of-
@@ -806,7 +809,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             const uint32_t tcol0 = lane_base + (uint32_t)(buf * P.acc_cols);
             // affine + ReLU + skip + store of one 8-channel block held in v[0..7]
             // (the skip operand is fetched by the caller BEFORE the TMEM wait: issued one at a time next to its use,
-            // every skip load costs a full DRAM round trip of this warp)
+            // every skip load costs a full DRAM round trip of this warp.  Tried and dropped in round 2: prefetch.global.L1
+            // of the step's skip vectors before the tfull wait -- epilogue work 3.6 k -> 2.9 k clk per step but the CTA
+            // slower, 5.1 k -> 6.5 k: the prefetch pass itself sits on this role's critical path; holding the first batch in
+            // registers across the wait spills at 64 registers.)
             auto store_with = [&](const uint32_t (&v)[8], uint32_t oidx, const uint4 &sk, const float2 (&scl)[4],
                                   const float2 (&shl)[4]) {
                 const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
@@ -1397,7 +1403,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
         return fail(MVS_ERR_UNSUPPORTED, "mvs_conv3d_c8_fwd: no tile configuration fits shared memory / TMEM for this layer");
     MVS_REQUIRE(!(out_f32 && skip_c8), "skip is not supported on the fp32 (Cout == 1) output");
     P.x_dw = (flags & MVS_X_DW) ? 1 : 0; P.y_dw = (flags & MVS_Y_DW) ? 1 : 0; P.skip_dw = (flags & MVS_SKIP_DW) ? 1 : 0;
-    MVS_REQUIRE(!P.x_dw || !P.tmerged, "MVS_X_DW: only the stride-2 / transposed layers read a W-de-interleaved input");
+    MVS_REQUIRE(!P.x_dw || g.mode == UM_CONV_S2, "MVS_X_DW: only the stride-2 layers read a W-de-interleaved input");
     MVS_REQUIRE(!P.y_dw || (P.tmerged && !out_f32), "MVS_Y_DW: only the stride-1 C8 layers write a W-de-interleaved output");
     MVS_REQUIRE(!P.skip_dw || skip_c8, "MVS_SKIP_DW without a skip tensor");
     MVS_REQUIRE(!P.skip_dw || P.tmerged || g.mode == UM_DECONV_S2, "MVS_SKIP_DW: stride-1 and transposed stride-2 layers only");

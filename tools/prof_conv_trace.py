@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--stages", default="1,2,3")
     ap.add_argument("--layers", default="conv0,conv2,conv4,prob")
     ap.add_argument("--ctas", type=int, default=4096)
+    ap.add_argument("--dw", type=int, default=1, help="W-de-interleaved layout flags as CostRegNet's fast path sets them")
     a = ap.parse_args()
     dev = "cuda:0"
     cfg = synth.CONFIGS["cfg3"]
@@ -40,7 +41,11 @@ def main():
             pk = ops.pack_conv_weights(wt, stride, tr)
             y0 = ops.conv3d_c8(x, pk, cin, cout, None, None, None, stride, tr, cout != 1)
             sk = torch.zeros_like(y0) if has_skip else None
-            fn = lambda: ops.conv3d_c8(x, pk, cin, cout, None, None, sk, stride, tr, cout != 1)
+            lay = 0
+            if a.dw:
+                lay = (_lib.X_DW if (stride == 2 and not tr) else 0) | (_lib.SKIP_DW if has_skip else 0) | \
+                      (_lib.Y_DW if name in ("conv0", "conv2", "conv4") else 0)
+            fn = lambda: ops.conv3d_c8(x, pk, cin, cout, None, None, sk, stride, tr, cout != 1, layout=lay)
             fn(); fn()
             buf = torch.zeros(a.ctas * 16, dtype=torch.int64, device=dev)
             lib.mvs_conv3d_c8_set_trace(buf.data_ptr(), a.ctas)
