@@ -498,6 +498,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     if (two) finish(q0, q1, q2, a1, n01);
                 }
             }
+            // (Round 2 experiment, dropped: reading the tap-0 partials first and handing the buffer back BEFORE the math and
+            // the stores -- the issuer of slab step + 4 waits for exactly this arrival -- made every T-merged layer 10-25 %
+            // SLOWER: epilogue work 569 -> 892 clk per step on `prob`, 897 -> 1303 on conv0 stage 3.  The MMAs then run
+            // concurrently with this role's TMEM reads and stores; serialised, as here, both are faster.)
             tc_fence_before();                                     // this thread's TMEM reads are complete ...
             mbar_arrive(tempty + (step & (UM_TBUFS - 1)));         // ... slab `step`'s buffer may be overwritten
             rt.lap(7);
