@@ -518,6 +518,12 @@ def main_ours(args, wl):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     stage_ms = [sum(a.elapsed_time(b) for a, b in ev[i::len(per_stage)]) / max(len(ev[i::len(per_stage)]), 1) for i in range(len(per_stage))]
+    per_gpu = [achieved]
+    if world > 1:                # every rank times its own builder launches: BASELINE configs[4] asks for the per-GPU figure
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = achieved
+        dist.all_reduce(t)
+        per_gpu = [float(v) for v in t.tolist()]
 
     if rank != 0:
         if world > 1:
@@ -570,7 +576,8 @@ def main_ours(args, wl):
                      "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                      "avg_launch_ms": kernel_ms / max(n_launch, 1), "launches_timed": n_launch,
                      "per_stage_ms": stage_ms, "per_stage_frac": [b / (t * 1e-3) / 1e9 / peak if t > 0 else None for b, t in zip(per_stage, stage_ms)],
-                     "share_of_step": kernel_ms / ms_eager if ms_eager > 0 else None},
+                     "share_of_step": kernel_ms / ms_eager if ms_eager > 0 else None,
+                     "per_gpu_achieved": per_gpu, "per_gpu_frac": [v / peak for v in per_gpu]},
         "clocks": clocks,
     }
     line["from_images"] = from_images
