@@ -65,7 +65,10 @@ constexpr int UM_MAX_LINES = 288;   // staged lines per slab (rows x channel blo
 #ifndef UM_MIN_CTAS
 #define UM_MIN_CTAS 2
 #endif
-constexpr int UM_TBUFS = 4;         // per-slab accumulator buffers of the T-merged mode
+#ifndef UM_TBUFS_LOG2
+#define UM_TBUFS_LOG2 2
+#endif
+constexpr int UM_TBUFS = 1 << UM_TBUFS_LOG2;    // per-slab accumulator buffers of the T-merged mode (a power of two)
 
 enum UmMode { UM_CONV_S1 = 0, UM_CONV_S2 = 1, UM_DECONV_S2 = 2 };
 
@@ -409,7 +412,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         for (int step = 0; step < nsteps; ++step) {
             // earlier slabs were waited for in earlier steps
             for (int sl = step == 0 ? 0 : step + 2; sl <= step + 2; ++sl)
-                mbar_wait(tfull + (sl & (UM_TBUFS - 1)), (uint32_t)(sl >> 2) & 1u);
+                mbar_wait(tfull + (sl & (UM_TBUFS - 1)), (uint32_t)(sl >> UM_TBUFS_LOG2) & 1u);
             rt.lap(6);
             tc_fence_after();
             uint32_t tcol[3];
@@ -661,8 +664,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 RoleTimer rt; rt.start(trace && lane == 0 && iss == 0, trace, 3);
                 int slot = iss, q = 0;                     // sl = q * ring + slot (ring is even and >= 2, so slot = iss < ring)
                 for (int sl = iss; sl < n_slabs; sl += 2) {
-                    const int buf = sl & (UM_TBUFS - 1), use = sl >> 2;
-                    static_assert(UM_TBUFS == 4, "use = sl >> 2");
+                    const int buf = sl & (UM_TBUFS - 1), use = sl >> UM_TBUFS_LOG2;
                     mbar_wait(full + slot, (uint32_t)q & 1u);
                     rt.lap(3);
                     if (use >= 1) mbar_wait(tempty + buf, (uint32_t)(use - 1) & 1u);
