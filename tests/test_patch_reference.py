@@ -39,6 +39,8 @@ def test_patch_mvsnet():
     run("MVSNet", "", "from models import mvsnet, module",
         "sorted(mvsnet.MVSNet(refine=False).state_dict())",
         "assert mvsnet.homo_warping is mvs_b200.ops.homo_warping and module.homo_warping is mvs_b200.ops.homo_warping\n"
+        "assert mvsnet.MVSNet is mvs_b200.mvsnet.MVSNet and models.MVSNet is mvs_b200.mvsnet.MVSNet\n"
+        "assert mvsnet.FeatureNet is mvs_b200.mvsnet.FeatureNet\n"
         "m = mvsnet.MVSNet(refine=False)\n"
         "assert type(m.cost_regularization).__module__ == 'mvs_b200.modules'\n"
         "assert sorted(m.state_dict()) == ref_keys")
