@@ -118,6 +118,7 @@ struct ConvPlan {
     int trace_ctas;
     uint32_t ring_magic;                            // (1 << 18) / ring + 1: x / ring == (x * ring_magic) >> 18 for x < 32768
     int tmerged, buf_cols;
+    int row_cols;                                   // T-merged: TMEM columns per output row of a slab buffer (3 n; 8 for n = 1)
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
@@ -129,6 +130,7 @@ struct ConvPlan {
 struct PackPlan {
     int cin, cout, n, cout_tiles, n_ksteps, nblk, transposed_weights, flip;
     int pad_rows;                 // all-zero rows appended to every chunk of a B block (T-merged, n = 8)
+    int grp_rows;                 // T-merged: rows per row-tap group (3 n real rows, the rest of the group zero); 0: no groups
     KStepSrc ks[UM_MAX_KSTEPS];   // [n_ksteps * nblk]: weight source of block `blk` of k-step `k` at [k * nblk + blk]
 };
 
@@ -384,7 +386,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int m = ew * 32 + lane;                                 // row of the M tile owned by this thread
         const uint32_t lane_base = taddr + ((uint32_t)(ew * 32) << 16);
         const size_t vol_o = (size_t)P.Dor * P.Hor * P.Wo;
-        const int n3 = 3 * P.n, nb = P.n >> 3, nb_shift = nb == 4 ? 2 : (nb == 2 ? 1 : 0);
+        const int n3 = P.row_cols, nb = P.n >> 3, nb_shift = nb == 4 ? 2 : (nb == 2 ? 1 : 0);
         const int my_rows = (P.ht - eg + 1) >> 1, n_items = my_rows * nb;
         const int ow = m0 + m;
         // output index of (row a, step): pos0 + a * row_stride + step * step_stride  (hoisted 64-bit arithmetic)
@@ -944,14 +946,17 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, uint16_t *__restrict__ out, int f16)
 {
-    const int rows_pc = P.nblk * P.n + P.pad_rows;               // rows per K chunk of a B block
+    const int grp = P.grp_rows > 0 ? P.grp_rows : P.nblk * P.n;  // T-merged: three row-tap groups of grp rows, 3 n of them real
+    const int n_grp = P.grp_rows > 0 ? 3 : 1, real_pg = P.grp_rows > 0 ? 3 * P.n : P.nblk * P.n;
+    const int rows_pc = n_grp * grp + P.pad_rows;                // rows per K chunk of a B block
     const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * rows_pc * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long t = i;
         const int e = (int)(t % 8); t /= 8;
         const int rr = (int)(t % rows_pc); t /= rows_pc;
-        if (rr >= P.nblk * P.n) { out[i] = 0; continue; }
-        const int row = rr % P.n, blk = rr / P.n;
+        const int gi = rr / grp, within = rr - gi * grp;
+        if (gi >= n_grp || within >= real_pg) { out[i] = 0; continue; }
+        const int row = within % P.n, blk = gi * (real_pg / P.n) + within / P.n;
         const int j = (int)(t % 2); t /= 2;
         const int ks = (int)(t % P.n_ksteps);
         const int ct = (int)(t / P.n_ksteps);
@@ -978,6 +983,7 @@ struct LayerGeom {
     int mode, cin_chunks, n, cout_tiles, arr;
     int nblk;                            // 3: stride-1 layers merge the three kh taps of an input row into one MMA
     int tmerged, pad_rows;               // T-merged: nblk = 9 (row tap 2,1,0 major, step tap 0,1,2 minor) [+ zero rows]
+    int row_cols;                        // T-merged: B rows per row-tap group = TMEM columns per output row (3 n; 8 for n = 1)
     std::vector<KStep> ks;
     std::vector<KStepSrc> srcs;          // [ks.size() * nblk]
 };
@@ -1012,21 +1018,27 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
         g.srcs.push_back(k.src);
     };
     g.nblk = g.mode == UM_CONV_S1 ? 3 : 1;
-    g.tmerged = 0; g.pad_rows = 0;
+    g.tmerged = 0; g.pad_rows = 0; g.row_cols = 0;
     static const int no_tmerged = getenv("MVS_UMMA_NO_TMERGED") ? atoi(getenv("MVS_UMMA_NO_TMERGED")) : 0;   // A/B knob
     if (g.mode == UM_CONV_S1 && !no_tmerged) {
         // T-merged candidate: n = 8 for Cout <= 8 (N = rows*24 is padded to a multiple of 16 with 8 zero B rows), else
         // Cout tiles of n = 32 or 16 (Cout padded to 16).  Taken when the packed weights of one Cout tile + a 2-deep ring
         // of 3-row slabs fit shared memory (Cin = 64 -> 64: four tiles of 16).
-        int n = Cout <= 8 ? 8 : (n_full > 32 ? 32 : n_full);
+        // Cout = 1 (`prob`, fp32 logits out): ONE column per (row tap, step tap) -- N = 16 per MMA (9 real columns + zero B
+        // rows) instead of 72, three TMEM columns per output row instead of 24, so up to 16 rows fit a buffer
+        int n = Cout == 1 ? 1 : (Cout <= 8 ? 8 : (n_full > 32 ? 32 : n_full));
         const int ksteps = CH == 1 ? 2 : 3 * ((CH + 1) / 2);
         const size_t slab3 = (size_t)3 * CH * UM_COLS * 16;
-        auto wbytes_of = [&](int nn) { return (size_t)ksteps * 2 * (9 * nn + (nn == 8 ? 8 : 0)) * 16; };
+        // n = 1: a row-tap group is padded to 8 B rows / 8 TMEM columns -- the accumulator column of an MMA must stay 8-aligned
+        // (three-column groups fault with "misaligned address")
+        auto pad_of = [](int nn) { return nn <= 8 ? 8 : 0; };                     // zero B rows behind the tap groups
+        auto cols_of = [](int nn) { return nn == 1 ? 8 : 3 * nn; };
+        auto wbytes_of = [&](int nn) { return (size_t)ksteps * 2 * (3 * cols_of(nn) + pad_of(nn)) * 16; };
         if (n == 32 && wbytes_of(32) + 2 * slab3 + 8192 > 226 * 1024) n = 16;
-        const int pad = n == 8 ? 8 : 0;
+        const int pad = pad_of(n);
         const size_t wbytes = wbytes_of(n);
         if (wbytes + 2 * slab3 + 8192 <= 226 * 1024 && ksteps * 9 <= UM_MAX_KSTEPS) {
-            g.tmerged = 1; g.pad_rows = pad; g.n = n; g.cout_tiles = Cout <= 8 ? 1 : (n_full + n - 1) / n; g.nblk = 9;
+            g.tmerged = 1; g.pad_rows = pad; g.row_cols = cols_of(n); g.n = n; g.cout_tiles = Cout <= 8 ? 1 : (n_full + n - 1) / n; g.nblk = 9;
             auto add9 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1) {
                 KStep k{0, 0, 0, col, chunk, lbo, 0, {{0, 0}, {0, 0}}};
                 g.ks.push_back(k);
@@ -1135,12 +1147,13 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         P.mode = g.mode; P.arr = 1; P.tmerged = 1;
         P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip; P.f16 = (flags & MVS_ACT_F16) ? 1 : 0;
         P.rd = 3; P.d_mul = 1;
-        const int rows_pc = 9 * g.n + g.pad_rows, n3 = 3 * g.n;
+        const int rows_pc = 3 * g.row_cols + g.pad_rows, n3 = g.row_cols;
+        P.row_cols = g.row_cols;
         const int packed_units = (int)g.ks.size() * 2 * rows_pc;
         // rows per CTA: minimise the staged (and multiplied) rows, row_blocks * (ht + 2); ring: as deep as fits
         int best = 0, best_ring = 0;
         long long best_cost = -1;
-        for (int ht = 8; ht >= 1; --ht) {
+        for (int ht = g.n == 1 ? UM_MAX_ACC : 8; ht >= 1; --ht) {
             if (ht > H && ht > 1) continue;
             const int buf_cols = round_up(ht * n3 + g.pad_rows, 16);
             if (UM_TBUFS * buf_cols > 512 || buf_cols > 256) continue;
@@ -1183,8 +1196,8 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
                 const KStep &ks = g.ks[k];
                 const int a_off = (i * g.cin_chunks + ks.chunk) * UM_COLS + ks.col;
                 const int b_off = (int)k * 2 * rows_pc + blk0 * n3;
-                // N is rounded up to a multiple of 16 (n = 8 only): the extra 8 columns either read the zero pad rows
-                // of the B block or land in the spare columns behind the last row of this buffer
+                // N is rounded up to a multiple of 16 (n = 8: +8 columns; n = 1: 3 / 6 / 9 -> 16): the extra columns either
+                // read the zero pad rows of the B block or land in the spare columns behind the last row of this buffer
                 const int n_mma = round_up(cnt * n3, 16);
                 if (ks.lbo > 0x3FFF || a_off > 0xFFFF || b_off > 0x3FFF || rows_pc > 0x3FFF) return false;
                 if (lo * n3 + n_mma > P.buf_cols) return false;
@@ -1361,7 +1374,7 @@ extern "C" int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stri
 {
     if (Cin <= 0 || Cout <= 0 || (stride != 1 && stride != 2)) return -1;
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
-    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * (g.nblk * g.n + g.pad_rows) * 16;
+    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * ((g.tmerged ? 3 * g.row_cols : g.nblk * g.n) + g.pad_rows) * 16;
 }
 
 extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride, int transposed,
@@ -1384,7 +1397,8 @@ extern "C" int mvs_conv3d_c8_pack_weights_ex(const float *w, void *packed, int C
     pp.flip = (transposed && stride == 1) ? 1 : 0;       // ConvTranspose3d(stride 1, pad 1) == conv with flipped taps
     for (size_t k = 0; k < g.srcs.size(); ++k) pp.ks[k] = g.srcs[k];
     pp.pad_rows = g.pad_rows;
-    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * (g.nblk * g.n + g.pad_rows) * 8;
+    pp.grp_rows = g.tmerged ? g.row_cols : 0;
+    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * ((g.tmerged ? 3 * g.row_cols : g.nblk * g.n) + g.pad_rows) * 8;
     pack_weights_kernel<<<cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         pp, w, (uint16_t *)packed, (flags & MVS_ACT_F16) ? 1 : 0);
     return check_launch("mvs_conv3d_c8_pack_weights");
