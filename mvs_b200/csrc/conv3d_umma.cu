@@ -131,6 +131,7 @@ struct PackPlan {
     int cin, cout, n, cout_tiles, n_ksteps, nblk, transposed_weights, flip;
     int pad_rows;                 // all-zero rows appended to every chunk of a B block (T-merged, n = 8)
     int grp_rows;                 // T-merged: rows per row-tap group (3 n real rows, the rest of the group zero); 0: no groups
+    int n_grp;                    // T-merged: groups per block (3; 4 with paired input rows)
     KStepSrc ks[UM_MAX_KSTEPS];   // [n_ksteps * nblk]: weight source of block `blk` of k-step `k` at [k * nblk + blk]
 };
 
@@ -947,7 +948,7 @@ __global__ void __launch_bounds__(256)
 pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, uint16_t *__restrict__ out, int f16)
 {
     const int grp = P.grp_rows > 0 ? P.grp_rows : P.nblk * P.n;  // T-merged: three row-tap groups of grp rows, 3 n of them real
-    const int n_grp = P.grp_rows > 0 ? 3 : 1, real_pg = P.grp_rows > 0 ? 3 * P.n : P.nblk * P.n;
+    const int n_grp = P.grp_rows > 0 ? P.n_grp : 1, real_pg = P.grp_rows > 0 ? 3 * P.n : P.nblk * P.n;
     const int rows_pc = n_grp * grp + P.pad_rows;                // rows per K chunk of a B block
     const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * rows_pc * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -984,6 +985,7 @@ struct LayerGeom {
     int nblk;                            // 3: stride-1 layers merge the three kh taps of an input row into one MMA
     int tmerged, pad_rows;               // T-merged: nblk = 9 (row tap 2,1,0 major, step tap 0,1,2 minor) [+ zero rows]
     int row_cols;                        // T-merged: B rows per row-tap group = TMEM columns per output row (3 n; 8 for n = 1)
+    int n_grp;                           // T-merged: row-tap groups per B block: 3, or 4 when Cin = 8 pairs input rows (below)
     std::vector<KStep> ks;
     std::vector<KStepSrc> srcs;          // [ks.size() * nblk]
 };
@@ -1018,7 +1020,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
         g.srcs.push_back(k.src);
     };
     g.nblk = g.mode == UM_CONV_S1 ? 3 : 1;
-    g.tmerged = 0; g.pad_rows = 0; g.row_cols = 0;
+    g.tmerged = 0; g.pad_rows = 0; g.row_cols = 0; g.n_grp = 0;
     static const int no_tmerged = getenv("MVS_UMMA_NO_TMERGED") ? atoi(getenv("MVS_UMMA_NO_TMERGED")) : 0;   // A/B knob
     if (g.mode == UM_CONV_S1 && !no_tmerged) {
         // T-merged candidate: n = 8 for Cout <= 8 (N = rows*24 is padded to a multiple of 16 with 8 zero B rows), else
@@ -1027,31 +1029,42 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
         // Cout = 1 (`prob`, fp32 logits out): ONE column per (row tap, step tap) -- N = 16 per MMA (9 real columns + zero B
         // rows) instead of 72, three TMEM columns per output row instead of 24, so up to 16 rows fit a buffer
         int n = Cout == 1 ? 1 : (Cout <= 8 ? 8 : (n_full > 32 ? 32 : n_full));
-        const int ksteps = CH == 1 ? 2 : 3 * ((CH + 1) / 2);
+        const int ksteps = CH == 1 ? 4 : 3 * ((CH + 1) / 2);
         const size_t slab3 = (size_t)3 * CH * UM_COLS * 16;
         // n = 1: a row-tap group is padded to 8 B rows / 8 TMEM columns -- the accumulator column of an MMA must stay 8-aligned
         // (three-column groups fault with "misaligned address")
         auto pad_of = [](int nn) { return nn <= 8 ? 8 : 0; };                     // zero B rows behind the tap groups
         auto cols_of = [](int nn) { return nn == 1 ? 8 : 3 * nn; };
-        auto wbytes_of = [&](int nn) { return (size_t)ksteps * 2 * (3 * cols_of(nn) + pad_of(nn)) * 16; };
+        auto wbytes_of = [&](int nn) { return (size_t)ksteps * 2 * ((CH == 1 ? 4 : 3) * cols_of(nn) + pad_of(nn)) * 16; };
         if (n == 32 && wbytes_of(32) + 2 * slab3 + 8192 > 226 * 1024) n = 16;
         const int pad = pad_of(n);
         const size_t wbytes = wbytes_of(n);
-        if (wbytes + 2 * slab3 + 8192 <= 226 * 1024 && ksteps * 9 <= UM_MAX_KSTEPS) {
-            g.tmerged = 1; g.pad_rows = pad; g.row_cols = cols_of(n); g.n = n; g.cout_tiles = Cout <= 8 ? 1 : (n_full + n - 1) / n; g.nblk = 9;
-            auto add9 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1) {
+        if (wbytes + 2 * slab3 + 8192 <= 226 * 1024 && ksteps * (CH == 1 ? 12 : 9) <= UM_MAX_KSTEPS) {
+            g.tmerged = 1; g.pad_rows = pad; g.row_cols = cols_of(n); g.n = n; g.cout_tiles = Cout <= 8 ? 1 : (n_full + n - 1) / n;
+            g.n_grp = CH == 1 ? 4 : 3;
+            g.nblk = 3 * g.n_grp;
+            // a k-step: K chunk 0 = tap kw0 of an input row, chunk 1 = tap kw1 of the same row (shift1 = 0) or of the NEXT
+            // input row (shift1 = 1: its row-tap groups sit one group further along N); kw < 0 = zero weights
+            auto add9 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1, int shift1 = 0) {
                 KStep k{0, 0, 0, col, chunk, lbo, 0, {{0, 0}, {0, 0}}};
                 g.ks.push_back(k);
-                for (int krow = 2; krow >= 0; --krow)
+                for (int grp = 0; grp < g.n_grp; ++grp)
                     for (int t = 0; t < 3; ++t) {
-                        KStepSrc sc{{(int8_t)tap_index(t, krow, kw0), (int8_t)(kw1 >= 0 ? tap_index(t, krow, kw1) : -1)},
-                                    {(int8_t)ch0, (int8_t)ch1}};
+                        const int krow0 = 2 - grp, krow1 = 2 - (grp - shift1);          // row taps 2, 1, 0 along the groups
+                        const int t0 = (kw0 >= 0 && krow0 >= 0 && krow0 <= 2) ? tap_index(t, krow0, kw0) : -1;
+                        const int t1 = (kw1 >= 0 && krow1 >= 0 && krow1 <= 2) ? tap_index(t, krow1, kw1) : -1;
+                        KStepSrc sc{{(int8_t)t0, (int8_t)t1}, {(int8_t)ch0, (int8_t)ch1}};
                         g.srcs.push_back(sc);
                     }
             };
             if (CH == 1) {
-                add9(0, 0, 1, 0, 0, 1, 0);        // taps kw = 0, 1 on adjacent staged columns (LBO = 16 B)
-                add9(2, 0, 1, 2, 0, -1, 0);       // tap kw = 2 paired with zero weights
+                // Cin = 8: a tap is half a K = 16 step.  Two input rows i, i+1 share three steps instead of four:
+                //   ks[0] (i: kw 0, 1)   ks[2] (i: kw 2 | i+1: kw 0, A chunk 1 one staged row further)   ks[3] (i+1: kw 1, 2)
+                // and a last unpaired row takes ks[0] + ks[1] (kw 2 | zeros).  The shared step updates FOUR output rows.
+                add9(0, 0, 1, 0, 0, 1, 0);                    // ks[0]: kw 0, 1 on adjacent staged columns (LBO = 16 B)
+                add9(2, 0, 1, 2, 0, -1, 0);                   // ks[1]: kw 2 | zero weights
+                add9(2, 0, UM_COLS - 2, 2, 0, 0, 0, 1);       // ks[2]: kw 2 of row i | kw 0 of row i + 1
+                add9(1, 0, 1, 1, 0, 2, 0);                    // ks[3]: kw 1, 2
             } else {
                 for (int kw = 0; kw < 3; ++kw)
                     for (int sidx = 0; sidx < CH; sidx += 2) {
@@ -1147,7 +1160,8 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         P.mode = g.mode; P.arr = 1; P.tmerged = 1;
         P.relu = (flags & MVS_RELU) ? 1 : 0; P.out_f32 = out_f32; P.has_skip = has_skip; P.f16 = (flags & MVS_ACT_F16) ? 1 : 0;
         P.rd = 3; P.d_mul = 1;
-        const int rows_pc = 3 * g.row_cols + g.pad_rows, n3 = g.row_cols;
+        const int rows_pc = g.n_grp * g.row_cols + g.pad_rows, n3 = g.row_cols;
+        const bool pair_rows = g.n_grp == 4;
         P.row_cols = g.row_cols;
         const int packed_units = (int)g.ks.size() * 2 * rows_pc;
         // rows per CTA: minimise the staged (and multiplied) rows, row_blocks * (ht + 2); ring: as deep as fits
@@ -1157,7 +1171,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             if (ht > H && ht > 1) continue;
             const int buf_cols = round_up(ht * n3 + g.pad_rows, 16);
             if (UM_TBUFS * buf_cols > 512 || buf_cols > 256) continue;
-            if ((int)g.ks.size() * (ht + 2) + 1 > UM_MAX_OPS) continue;
+            if ((pair_rows ? 2 : (int)g.ks.size()) * (ht + 2) + 1 > UM_MAX_OPS) continue;
             int ring = 0;
             for (int r = UM_MAX_RING; r >= 2 && !ring; r -= 2)          // even: see the issuer role
                 if (plan_smem_bytes(packed_units + 2 * buf_cols, r, (ht + 2) * g.cin_chunks * UM_COLS) <= 226 * 1024) ring = r;
@@ -1188,22 +1202,34 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         // zero-initialise the slab's whole buffer (A: any staged finite bytes, B: the zero block), then one MMA per
         // (staged input row i, k-step): rows lo..hi of the tile get the row taps i - row, all three step taps at once
         P.ops[n_ops++] = entry(0, 1, packed_units, P.buf_cols, 0, P.buf_cols, 0);
-        for (int i = 0; i < P.rh; ++i) {
-            const int lo = i - 2 < 0 ? 0 : i - 2, hi = i > P.ht - 1 ? P.ht - 1 : i;
-            if (hi < lo) continue;
-            const int cnt = hi - lo + 1, blk0 = 2 - (i - lo);
-            for (size_t k = 0; k < g.ks.size(); ++k) {
-                const KStep &ks = g.ks[k];
-                const int a_off = (i * g.cin_chunks + ks.chunk) * UM_COLS + ks.col;
-                const int b_off = (int)k * 2 * rows_pc + blk0 * n3;
-                // N is rounded up to a multiple of 16 (n = 8: +8 columns; n = 1: 3 / 6 / 9 -> 16): the extra columns either
-                // read the zero pad rows of the B block or land in the spare columns behind the last row of this buffer
-                const int n_mma = round_up(cnt * n3, 16);
-                if (ks.lbo > 0x3FFF || a_off > 0xFFFF || b_off > 0x3FFF || rows_pc > 0x3FFF) return false;
-                if (lo * n3 + n_mma > P.buf_cols) return false;
-                P.ops[n_ops++] = entry(a_off, ks.lbo, b_off, rows_pc, lo * n3, n_mma, 1);
+        // one MMA: k-step k on staged input row i, updating output rows first .. first + span - 1 (clipped to the tile) with
+        // the row-tap groups that line up with them; group 0 of the block belongs to output row i - 2
+        bool ok = true;
+        auto emit = [&](int k, int i, int span) {
+            const int first = i - 2;
+            const int lo = first < 0 ? 0 : first, hi = first + span - 1 > P.ht - 1 ? P.ht - 1 : first + span - 1;
+            if (hi < lo) return;
+            const KStep &ks = g.ks[(size_t)k];
+            const int cnt = hi - lo + 1, grp0 = lo - first;
+            const int a_off = (i * g.cin_chunks + ks.chunk) * UM_COLS + ks.col;
+            const int b_off = k * 2 * rows_pc + grp0 * n3;
+            // N is rounded up to a multiple of 16 (n = 8: +8 columns; n = 1: 8 / 24 -> 16 / 32): the extra columns either
+            // read the zero pad rows of the B block or land in the spare columns behind the last row of this buffer
+            const int n_mma = round_up(cnt * n3, 16);
+            if (ks.lbo > 0x3FFF || a_off > 0xFFFF || b_off > 0x3FFF || rows_pc > 0x3FFF || n_ops >= UM_MAX_OPS ||
+                lo * n3 + n_mma > P.buf_cols || n_mma > 256) { ok = false; return; }
+            P.ops[n_ops++] = entry(a_off, ks.lbo, b_off, rows_pc, lo * n3, n_mma, 1);
+        };
+        if (pair_rows) {
+            for (int i = 0; i < P.rh; i += 2) {
+                if (i + 1 < P.rh) { emit(0, i, 3); emit(2, i, 4); emit(3, i + 1, 3); }
+                else { emit(0, i, 3); emit(1, i, 3); }
             }
+        } else {
+            for (int i = 0; i < P.rh; ++i)
+                for (size_t k = 0; k < g.ks.size(); ++k) emit((int)k, i, 3);
         }
+        if (!ok) return false;
         P.n_ops = n_ops;
         return true;
     }
@@ -1374,7 +1400,7 @@ extern "C" int64_t mvs_conv3d_c8_packed_weight_bytes(int Cin, int Cout, int stri
 {
     if (Cin <= 0 || Cout <= 0 || (stride != 1 && stride != 2)) return -1;
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
-    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * ((g.tmerged ? 3 * g.row_cols : g.nblk * g.n) + g.pad_rows) * 16;
+    return (int64_t)g.cout_tiles * (int64_t)g.ks.size() * 2 * ((g.tmerged ? g.n_grp * g.row_cols : g.nblk * g.n) + g.pad_rows) * 16;
 }
 
 extern "C" int mvs_conv3d_c8_pack_weights(const float *w, void *packed, int Cin, int Cout, int stride, int transposed,
@@ -1398,7 +1424,8 @@ extern "C" int mvs_conv3d_c8_pack_weights_ex(const float *w, void *packed, int C
     for (size_t k = 0; k < g.srcs.size(); ++k) pp.ks[k] = g.srcs[k];
     pp.pad_rows = g.pad_rows;
     pp.grp_rows = g.tmerged ? g.row_cols : 0;
-    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * ((g.tmerged ? 3 * g.row_cols : g.nblk * g.n) + g.pad_rows) * 8;
+    pp.n_grp = g.n_grp;
+    const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * ((g.tmerged ? g.n_grp * g.row_cols : g.nblk * g.n) + g.pad_rows) * 8;
     pack_weights_kernel<<<cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         pp, w, (uint16_t *)packed, (flags & MVS_ACT_F16) ? 1 : 0);
     return check_launch("mvs_conv3d_c8_pack_weights");
