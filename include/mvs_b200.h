@@ -49,6 +49,8 @@ extern "C" {
 #define MVS_X_DW 4096          /* conv3d_c8 (stride 2): x has W de-interleaved, column w at (w&1)*ceil(W/2) + (w>>1)      */
 #define MVS_Y_DW 8192          /* conv3d_c8 (stride 1): write y W-de-interleaved (for a stride-2 consumer / a skip add)    */
 #define MVS_SKIP_DW 16384      /* conv3d_c8: the skip tensor is W-de-interleaved                                            */
+#define MVS_KD1 32768          /* conv3d_c8 (stride 1): the weights are zero outside the centre depth tap (kd = 1) -- a 2D
+                                  convolution over D stacked images; the kernel skips the other depth taps' MMAs            */
 #define MVS_WARP_TMA 1024       /* C8 builder: force the TMA-staged kernel (fp16 maps only); neither bit: library picks */
 
 /* depth_mode */

@@ -1204,13 +1204,14 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         P.ops[n_ops++] = entry(0, 1, packed_units, P.buf_cols, 0, P.buf_cols, 0);
         // one MMA: k-step k on staged input row i, updating output rows first .. first + span - 1 (clipped to the tile) with
         // the row-tap groups that line up with them; group 0 of the block belongs to output row i - 2
+        // (skip: leading groups / output rows left out -- MVS_KD1 layers only have the centre row tap, group 1)
         bool ok = true;
-        auto emit = [&](int k, int i, int span) {
-            const int first = i - 2;
+        auto emit = [&](int k, int i, int span, int skip = 0) {
+            const int first = i - 2 + skip;
             const int lo = first < 0 ? 0 : first, hi = first + span - 1 > P.ht - 1 ? P.ht - 1 : first + span - 1;
             if (hi < lo) return;
             const KStep &ks = g.ks[(size_t)k];
-            const int cnt = hi - lo + 1, grp0 = lo - first;
+            const int cnt = hi - lo + 1, grp0 = lo - first + skip;
             const int a_off = (i * g.cin_chunks + ks.chunk) * UM_COLS + ks.col;
             const int b_off = k * 2 * rows_pc + grp0 * n3;
             // N is rounded up to a multiple of 16 (n = 8: +8 columns; n = 1: 8 / 24 -> 16 / 32): the extra columns either
@@ -1220,7 +1221,20 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
                 lo * n3 + n_mma > P.buf_cols || n_mma > 256) { ok = false; return; }
             P.ops[n_ops++] = entry(a_off, ks.lbo, b_off, rows_pc, lo * n3, n_mma, 1);
         };
-        if (pair_rows) {
+        if (flags & MVS_KD1) {
+            // weights are zero outside the centre row tap (a 2D convolution whose images ride the row axis): input row i only
+            // feeds output row i - 1 -- N = one group (two for the shared step of a row pair), and the halo rows 0 and
+            // rh - 1 are not multiplied at all
+            if (pair_rows) {
+                for (int i = 1; i + 1 < P.rh; i += 2) {
+                    if (i + 2 < P.rh) { emit(0, i, 1, 1); emit(2, i, 2, 1); emit(3, i + 1, 1, 1); }
+                    else { emit(0, i, 1, 1); emit(1, i, 1, 1); }
+                }
+            } else {
+                for (int i = 1; i + 1 < P.rh; ++i)
+                    for (size_t k = 0; k < g.ks.size(); ++k) emit((int)k, i, 1, 1);
+            }
+        } else if (pair_rows) {
             for (int i = 0; i < P.rh; i += 2) {
                 if (i + 1 < P.rh) { emit(0, i, 3); emit(2, i, 4); emit(3, i + 1, 3); }
                 else { emit(0, i, 3); emit(1, i, 3); }

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import modules, ops
+from . import _lib, modules, ops
 from .cascade import cascade_hot_path
 
 
@@ -155,10 +155,12 @@ class _NativeLayer:
         L = self.get()
         if folded:
             CB, N, H, W, _ = x.shape
-            y = ops.conv3d_c8(x.view(1, CB, N, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu, act_f16=True)
+            y = ops.conv3d_c8(x.view(1, CB, N, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu, act_f16=True,
+                              layout=_lib.KD1)
             return y.view(y.shape[1], N, H, W, 8)
         N, CB, H, W, _ = x.shape
-        y = ops.conv3d_c8(x.view(N, CB, 1, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu, act_f16=True)
+        y = ops.conv3d_c8(x.view(N, CB, 1, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu, act_f16=True,
+                              layout=_lib.KD1)
         return y.view(N, y.shape[1], H, W, 8)
 
 

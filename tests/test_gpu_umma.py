@@ -131,6 +131,28 @@ def test_conv3d_c8_dw_layout(which, cin, cout, stride, transposed, dhw):
     assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
 
 
+@pytest.mark.parametrize("cin,cout,dhw", [(8, 8, (5, 9, 150)), (8, 8, (1, 7, 40)), (16, 16, (4, 6, 130)), (32, 8, (5, 5, 64)),
+                                          (64, 32, (3, 4, 40))])
+def test_conv3d_c8_kd1(cin, cout, dhw):
+    """MVS_KD1 (weights zero outside kd = 1: D stacked images, the FeatureNet engine's form): the kernel skips the other depth
+    taps' MMAs and the halo rows -- only exact zeros leave the sums, so the result is bit-identical to the unflagged run."""
+    from mvs_b200 import ops, _lib as L
+    rng = np.random.RandomState(5 + cin + cout)
+    D, H, W = dhw
+    x = torch.from_numpy(rng.standard_normal((1, (cin + 7) // 8, D, H, W, 8)).astype(np.float32)).to(DEV).half()
+    w = np.zeros((cout, cin, 3, 3, 3), np.float32)
+    w[:, :, 1] = rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(9 * cin)
+    packed = ops.pack_conv_weights(cu(w), 1, False, act_f16=True)
+    scale, shift = cu(rng.uniform(0.5, 1.5, cout).astype(np.float32)), cu((0.3 * rng.standard_normal(cout)).astype(np.float32))
+    ref = ops.conv3d_c8(x, packed, cin, cout, scale, shift, None, 1, False, True, act_f16=True)
+    out = ops.conv3d_c8(x, packed, cin, cout, scale, shift, None, 1, False, True, act_f16=True, layout=L.KD1)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+    # and images do not mix: every depth slice equals the same layer run on that slice alone
+    one = ops.conv3d_c8(x[:, :, :1].contiguous(), packed, cin, cout, scale, shift, None, 1, False, True, act_f16=True, layout=L.KD1)
+    assert torch.equal(one.view(torch.int16), out[:, :, :1].contiguous().view(torch.int16))
+
+
 def test_conv3d_c8_dw_flag_validation():
     from mvs_b200 import ops, _lib as L
     x = torch.zeros(1, 1, 2, 4, 16, 8, dtype=torch.bfloat16, device=DEV)
