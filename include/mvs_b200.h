@@ -51,6 +51,8 @@ extern "C" {
 #define MVS_SKIP_DW 16384      /* conv3d_c8: the skip tensor is W-de-interleaved                                            */
 #define MVS_KD1 32768          /* conv3d_c8 (stride 1): the weights are zero outside the centre depth tap (kd = 1) -- a 2D
                                   convolution over D stacked images; the kernel skips the other depth taps' MMAs            */
+#define MVS_FLAT2D 65536       /* conv3d_c8 + pack_weights_ex (stride 1, D = 1): plain 2D convolution with the centre depth slice of
+                                  the weights; the kernel tiles the image rows instead of a depth axis (no step-tap partials)  */
 #define MVS_WARP_TMA 1024       /* C8 builder: force the TMA-staged kernel (fp16 maps only); neither bit: library picks */
 
 /* depth_mode */

@@ -25,6 +25,7 @@ WARP_NO_TMA = 512
 WARP_TMA = 1024
 ACT_F16 = 2048
 X_DW, Y_DW, SKIP_DW = 4096, 8192, 16384      # conv3d_c8: W-de-interleaved input / output / skip tensor
+FLAT2D = 65536                               # conv3d_c8 / pack: plain 2D convolution (D = 1), image rows tiled by the kernel
 KD1 = 32768                                  # conv3d_c8: weights zero outside the centre depth tap (stacked 2D images)
 DEPTH_PLANE = 0
 DEPTH_PIXEL = 1

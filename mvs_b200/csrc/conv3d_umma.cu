@@ -119,6 +119,10 @@ struct ConvPlan {
     uint32_t ring_magic;                            // (1 << 18) / ring + 1: x / ring == (x * ring_magic) >> 18 for x < 32768
     int tmerged, buf_cols;
     int row_cols;                                   // T-merged: TMEM columns per output row of a slab buffer (3 n; 8 for n = 1)
+    // flat 2D mode (MVS_FLAT2D; real D = 1, one image per batch element): a slab is a block of ht + 2 consecutive IMAGE rows
+    // and the step axis walks the row blocks of the image.  The kh taps ride the row-tap groups, there are NO step taps: an
+    // output step reads one buffer, one partial (n TMEM columns per row instead of 3 n -> up to 15 rows per step for n = 8).
+    int flat2d;
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
@@ -132,6 +136,7 @@ struct PackPlan {
     int pad_rows;                 // all-zero rows appended to every chunk of a B block (T-merged, n = 8)
     int grp_rows;                 // T-merged: rows per row-tap group (3 n real rows, the rest of the group zero); 0: no groups
     int n_grp;                    // T-merged: groups per block (3; 4 with paired input rows)
+    int n_t;                      // T-merged: step taps per group (3; 1 in flat 2D mode)
     KStepSrc ks[UM_MAX_KSTEPS];   // [n_ksteps * nblk]: weight source of block `blk` of k-step `k` at [k * nblk + blk]
 };
 
@@ -376,7 +381,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     tc_fence_after();
     const uint32_t taddr = *tmem_slot;
     if (trace && tid == 0) { trace[9] = clock64() - t_cta0; trace[10] = nsteps; }
-    const int n_slabs = TM ? nsteps + 2 : P.d_mul * (nsteps - 1) + P.rd;   // slabs this CTA stages in total
+    const int n_slabs = TM ? (P.flat2d ? nsteps : nsteps + 2) : P.d_mul * (nsteps - 1) + P.rd;   // slabs this CTA stages in total
 
     if (TM && (warp < 4 || warp >= 12)) {
         // =========================== T-merged epilogue: TMEM -> registers -> global =====================
@@ -392,7 +397,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int ow = m0 + m;
         // output index of (row a, step): pos0 + a * row_stride + step * step_stride  (hoisted 64-bit arithmetic)
         const size_t plane_o = (size_t)P.Hor * P.Wo;
-        const size_t row_stride = P.swap ? plane_o : (size_t)P.Wo, step_stride = P.swap ? (size_t)P.Wo : plane_o;
+        const size_t row_stride = (P.swap && !P.flat2d) ? plane_o : (size_t)P.Wo;
+        const size_t step_stride = P.flat2d ? (size_t)P.ht * P.Wo : (P.swap ? (size_t)P.Wo : plane_o);
         const size_t pos00 = (size_t)h0 * row_stride + (size_t)step_begin * step_stride;
         const size_t pos0 = pos00 + (size_t)ow;
         const bool w_ok = ow < P.Wo;
@@ -413,6 +419,43 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         }
         RoleTimer rt; rt.start(trace && tid == 0, trace, 6);
         for (int step = 0; step < nsteps; ++step) {
+            if (P.flat2d) {
+                // ---- flat 2D: one slab, one partial per output row block ----
+                mbar_wait(tfull + (step & (UM_TBUFS - 1)), (uint32_t)(step >> UM_TBUFS_LOG2) & 1u);
+                rt.lap(6);
+                tc_fence_after();
+                const uint32_t tc = lane_base + (uint32_t)((step & (UM_TBUFS - 1)) * P.buf_cols);
+                const uint32_t so = (uint32_t)step * ss32;
+                const int row_lim = P.Hr - (step_begin + step) * P.ht;            // image rows left in this block
+                for (int it = 0; it < n_items; it += 4) {
+                    uint32_t q[4][8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (it + j < n_items)
+                            tmem_ld8_nowait(tc + (uint32_t)((eg + 2 * ((it + j) >> nb_shift)) * n3 + ((it + j) & (nb - 1)) * 8), q[j]);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (it + j >= n_items) break;
+                        const int a = eg + 2 * ((it + j) >> nb_shift), n0 = ((it + j) & (nb - 1)) * 8;
+                        if (!w_ok || a >= row_lim || ct * nb + (n0 >> 3) >= P.cout_chunks) continue;
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 v = __ffma2_rn(make_float2(__uint_as_float(q[j][2 * e]), __uint_as_float(q[j][2 * e + 1])),
+                                                  make_float2(s_scale[n0 + 2 * e], s_scale[n0 + 2 * e + 1]),
+                                                  make_float2(s_shift[n0 + 2 * e], s_shift[n0 + 2 * e + 1]));
+                            if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                            pk[e] = P.f16 ? pack_f16x2(v.x, v.y) : pack_bf16x2(v.x, v.y);
+                        }
+                        ybase[so + (uint32_t)a * rs32 + (uint32_t)(n0 >> 3) * vo32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty + (step & (UM_TBUFS - 1)));
+                rt.lap(7);
+                continue;
+            }
             // earlier slabs were waited for in earlier steps
             for (int sl = step == 0 ? 0 : step + 2; sl <= step + 2; ++sl)
                 mbar_wait(tfull + (sl & (UM_TBUFS - 1)), (uint32_t)(sl >> UM_TBUFS_LOG2) & 1u);
@@ -536,6 +579,58 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         // (Stride-2 layers over a W-de-interleaved input, x_dw: their cp.async lanes read contiguous 16 B vectors, 4 L1
         // wavefronts per instruction instead of 8.  One bulk copy per staged line was tried on top of that and is not
         // faster -- conv1 unchanged, the multi-chunk conv3 / conv5 10-25 % slower: 2-3 UBLKCP per lane and slab.)
+        if (TM && P.flat2d) {
+            // flat 2D: slab i = image rows (step_begin + i) * ht - 1 .. + ht of every channel block; one bulk copy per line,
+            // rows above / below the image (first / last block) and the column halo are zero-filled
+            RoleTimer rt; rt.start(trace && tid == 128, trace, 1);
+            const int c_lo = m0 == 0 ? 1 : 0;                                  // column c holds w = m0 - 1 + c
+            const int c_hi = min(UM_COLS, P.W - m0 + 1);
+            const int ln = pwarp + NPW * lane;
+            const int my_row = ln / P.cin_chunks, my_chunk = ln % P.cin_chunks;
+            const bool has_line = ln < lines && c_hi > c_lo;
+            const uint32_t my_bytes = has_line ? (uint32_t)(c_hi - c_lo) * 16u : 0u;
+            uint32_t full_bytes = my_bytes;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) full_bytes += __shfl_xor_sync(0xffffffffu, full_bytes, o);
+            const long long src0 = (((long long)b * P.cin_chunks + my_chunk) * P.Hr + (my_row - 1)) * (long long)P.W + (m0 - 1 + c_lo);
+            const uint32_t my_dst_off = (uint32_t)ln * UM_COLS + (uint32_t)c_lo;
+            const bool edge_cols = c_lo > 0 || c_hi < UM_COLS;
+            int slot = 0, q = 0;
+            for (int i = 0; i < n_slabs; ++i, slot = slot + 1 == P.ring ? 0 : slot + 1, q += slot == 0 ? 1 : 0) {
+                if (q >= 1) mbar_wait(empty + slot, (uint32_t)(q - 1) & 1u);
+                rt.lap(1);
+                const int blk = step_begin + i;
+                const int row0 = blk * P.ht - 1;                                // image row of staged row 0
+                const bool clipped = row0 < 0 || row0 + P.rh > P.Hr;
+                const bool my_ok = my_bytes != 0 && (unsigned)(row0 + my_row) < (unsigned)P.Hr;
+                uint4 *slab = sa + (size_t)slot * P.slab_units;
+                uint32_t warp_bytes = full_bytes;
+                if (edge_cols || clipped) {
+                    for (int l2 = pwarp; l2 < lines; l2 += NPW) {
+                        const bool row_ok = (unsigned)(row0 + l2 / P.cin_chunks) < (unsigned)P.Hr;
+                        uint4 *dst = slab + (size_t)l2 * UM_COLS;
+                        if (!row_ok) {
+                            for (int c = lane; c < UM_COLS; c += 32) dst[c] = make_uint4(0, 0, 0, 0);
+                        } else {
+                            if (lane < c_lo) dst[lane] = make_uint4(0, 0, 0, 0);
+                            for (int c = c_hi + lane; c < UM_COLS; c += 32) dst[c] = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                    fence_async_smem();
+                    if (clipped) {
+                        warp_bytes = my_ok ? my_bytes : 0u;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) warp_bytes += __shfl_xor_sync(0xffffffffu, warp_bytes, o);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) mbar_arrive_expect_tx(full + slot, warp_bytes);
+                __syncwarp();
+                if (my_ok) bulk_copy_g2s(slab + my_dst_off, x + (src0 + (long long)blk * P.ht * P.W), my_bytes, full + slot);
+                rt.lap(2);
+            }
+            rt.flush();
+        } else
         if (TM) {
             // A staged line (one row of one channel block, 132 consecutive voxels) is contiguous in global memory, so it
             // moves as ONE bulk copy issued by one lane (lane l of producer warp p owns line p + 4 l); only the out-of-
@@ -948,7 +1043,7 @@ __global__ void __launch_bounds__(256)
 pack_weights_kernel(const __grid_constant__ PackPlan P, const float *__restrict__ w, uint16_t *__restrict__ out, int f16)
 {
     const int grp = P.grp_rows > 0 ? P.grp_rows : P.nblk * P.n;  // T-merged: three row-tap groups of grp rows, 3 n of them real
-    const int n_grp = P.grp_rows > 0 ? P.n_grp : 1, real_pg = P.grp_rows > 0 ? 3 * P.n : P.nblk * P.n;
+    const int n_grp = P.grp_rows > 0 ? P.n_grp : 1, real_pg = P.grp_rows > 0 ? P.n_t * P.n : P.nblk * P.n;
     const int rows_pc = n_grp * grp + P.pad_rows;                // rows per K chunk of a B block
     const long long total = (long long)P.cout_tiles * P.n_ksteps * 2 * rows_pc * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -986,6 +1081,7 @@ struct LayerGeom {
     int tmerged, pad_rows;               // T-merged: nblk = 9 (row tap 2,1,0 major, step tap 0,1,2 minor) [+ zero rows]
     int row_cols;                        // T-merged: B rows per row-tap group = TMEM columns per output row (3 n; 8 for n = 1)
     int n_grp;                           // T-merged: row-tap groups per B block: 3, or 4 when Cin = 8 pairs input rows (below)
+    int n_t;                             // T-merged: step taps per group (3; 1 in flat 2D mode)
     std::vector<KStep> ks;
     std::vector<KStepSrc> srcs;          // [ks.size() * nblk]
 };
@@ -1001,7 +1097,7 @@ static int tap_index(int k_step, int k_row, int kw)
     return (kd * 3 + kh) * 3 + kw;
 }
 
-static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
+static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed, bool flat2d = false)
 {
     LayerGeom g;
     g.mode = transposed ? (stride == 2 ? UM_DECONV_S2 : UM_CONV_S1) : (stride == 2 ? UM_CONV_S2 : UM_CONV_S1);
@@ -1020,7 +1116,7 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
         g.srcs.push_back(k.src);
     };
     g.nblk = g.mode == UM_CONV_S1 ? 3 : 1;
-    g.tmerged = 0; g.pad_rows = 0; g.row_cols = 0; g.n_grp = 0;
+    g.tmerged = 0; g.pad_rows = 0; g.row_cols = 0; g.n_grp = 0; g.n_t = 0;
     static const int no_tmerged = getenv("MVS_UMMA_NO_TMERGED") ? atoi(getenv("MVS_UMMA_NO_TMERGED")) : 0;   // A/B knob
     if (g.mode == UM_CONV_S1 && !no_tmerged) {
         // T-merged candidate: n = 8 for Cout <= 8 (N = rows*24 is padded to a multiple of 16 with 8 zero B rows), else
@@ -1034,25 +1130,29 @@ static LayerGeom make_geom(int Cin, int Cout, int stride, int transposed)
         // n = 1: a row-tap group is padded to 8 B rows / 8 TMEM columns -- the accumulator column of an MMA must stay 8-aligned
         // (three-column groups fault with "misaligned address")
         auto pad_of = [](int nn) { return nn <= 8 ? 8 : 0; };                     // zero B rows behind the tap groups
-        auto cols_of = [](int nn) { return nn == 1 ? 8 : 3 * nn; };
+        const int n_t = flat2d ? 1 : 3;               // flat 2D: no step taps, a row-tap group is n rows / n TMEM columns
+        auto cols_of = [&](int nn) { return nn == 1 ? 8 : n_t * nn; };
         auto wbytes_of = [&](int nn) { return (size_t)ksteps * 2 * ((CH == 1 ? 4 : 3) * cols_of(nn) + pad_of(nn)) * 16; };
         if (n == 32 && wbytes_of(32) + 2 * slab3 + 8192 > 226 * 1024) n = 16;
         const int pad = pad_of(n);
         const size_t wbytes = wbytes_of(n);
-        if (wbytes + 2 * slab3 + 8192 <= 226 * 1024 && ksteps * (CH == 1 ? 12 : 9) <= UM_MAX_KSTEPS) {
+        if (wbytes + 2 * slab3 + 8192 <= 226 * 1024 && ksteps * (CH == 1 ? 4 : 3) * n_t <= UM_MAX_KSTEPS && !(flat2d && n == 1)) {
             g.tmerged = 1; g.pad_rows = pad; g.row_cols = cols_of(n); g.n = n; g.cout_tiles = Cout <= 8 ? 1 : (n_full + n - 1) / n;
             g.n_grp = CH == 1 ? 4 : 3;
-            g.nblk = 3 * g.n_grp;
+            g.n_t = n_t;
+            g.nblk = n_t * g.n_grp;
             // a k-step: K chunk 0 = tap kw0 of an input row, chunk 1 = tap kw1 of the same row (shift1 = 0) or of the NEXT
             // input row (shift1 = 1: its row-tap groups sit one group further along N); kw < 0 = zero weights
             auto add9 = [&](int col, int chunk, int lbo, int kw0, int ch0, int kw1, int ch1, int shift1 = 0) {
                 KStep k{0, 0, 0, col, chunk, lbo, 0, {{0, 0}, {0, 0}}};
                 g.ks.push_back(k);
+                // flat 2D: the groups carry the kh taps of the centre depth slice (kd = 1), there is no step tap
+                auto tap_of = [&](int t, int krow, int kw) { return flat2d ? tap_index(krow, 1, kw) : tap_index(t, krow, kw); };
                 for (int grp = 0; grp < g.n_grp; ++grp)
-                    for (int t = 0; t < 3; ++t) {
+                    for (int t = 0; t < n_t; ++t) {
                         const int krow0 = 2 - grp, krow1 = 2 - (grp - shift1);          // row taps 2, 1, 0 along the groups
-                        const int t0 = (kw0 >= 0 && krow0 >= 0 && krow0 <= 2) ? tap_index(t, krow0, kw0) : -1;
-                        const int t1 = (kw1 >= 0 && krow1 >= 0 && krow1 <= 2) ? tap_index(t, krow1, kw1) : -1;
+                        const int t0 = (kw0 >= 0 && krow0 >= 0 && krow0 <= 2) ? tap_of(t, krow0, kw0) : -1;
+                        const int t1 = (kw1 >= 0 && krow1 >= 0 && krow1 <= 2) ? tap_of(t, krow1, kw1) : -1;
                         KStepSrc sc{{(int8_t)t0, (int8_t)t1}, {(int8_t)ch0, (int8_t)ch1}};
                         g.srcs.push_back(sc);
                     }
@@ -1167,8 +1267,11 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         // rows per CTA: minimise the staged (and multiplied) rows, row_blocks * (ht + 2); ring: as deep as fits
         int best = 0, best_ring = 0;
         long long best_cost = -1;
-        for (int ht = g.n == 1 ? UM_MAX_ACC : 8; ht >= 1; --ht) {
-            if (ht > H && ht > 1) continue;
+        const bool flat2d = (flags & MVS_FLAT2D) != 0;   // rows of a slab = image rows; D (the step extent) is the image height
+        P.flat2d = flat2d ? 1 : 0;
+        const int rows_ext = flat2d ? D : H;             // extent the ht-row blocks tile
+        for (int ht = (g.n == 1 || flat2d) ? UM_MAX_ACC : 8; ht >= 1; --ht) {
+            if (ht > rows_ext && ht > 1) continue;
             const int buf_cols = round_up(ht * n3 + g.pad_rows, 16);
             if (UM_TBUFS * buf_cols > 512 || buf_cols > 256) continue;
             if ((pair_rows ? 2 : (int)g.ks.size()) * (ht + 2) + 1 > UM_MAX_OPS) continue;
@@ -1177,7 +1280,8 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
                 if (plan_smem_bytes(packed_units + 2 * buf_cols, r, (ht + 2) * g.cin_chunks * UM_COLS) <= 226 * 1024) ring = r;
             if (!ring) continue;
             // a 2-deep ring leaves each issuer one slot: its next slab cannot load while the current one is multiplied
-            const long long cost = (long long)((H + ht - 1) / ht) * (ht + 2) * (ring < 4 ? 10 : 8);
+            // (flat 2D: every block is a pipeline step of its own -- charge the per-step overhead, ~4 rows' worth)
+            const long long cost = (long long)((rows_ext + ht - 1) / ht) * (ht + 2 + (flat2d ? 4 : 0)) * (ring < 4 ? 10 : 8);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ht; best_ring = ring; }
         }
         if (!best) return false;
@@ -1192,7 +1296,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
         while (cols < UM_TBUFS * P.buf_cols) cols *= 2;
         P.tmem_cols = cols;
         P.h_mul = 1; P.h_base = -1; P.d_base = -1; P.w_step = 1; P.w_base[0] = -1; P.w_base[1] = -1;
-        P.od_mul = 1; P.oh_mul = 1; P.w_mul = 1; P.steps = P.Do;
+        P.od_mul = 1; P.oh_mul = 1; P.w_mul = 1; P.steps = flat2d ? (D + P.ht - 1) / P.ht : P.Do;
         P.n_issuers = 1;
         auto entry = [&](int a_off, int a_lbo, int b_off, int b_lbo, int col, int n_mma, int accumulate) {
             return make_uint4((uint32_t)a_off | ((uint32_t)a_lbo << 16), (uint32_t)b_off | ((uint32_t)b_lbo << 16), (uint32_t)col,
@@ -1428,7 +1532,10 @@ extern "C" int mvs_conv3d_c8_pack_weights_ex(const float *w, void *packed, int C
 {
     MVS_REQUIRE(w && packed, "null pointer");
     MVS_REQUIRE(Cin > 0 && Cout > 0 && (stride == 1 || stride == 2), "bad layer shape");
-    const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
+    const bool flat2d = (flags & MVS_FLAT2D) != 0;
+    MVS_REQUIRE(!flat2d || (stride == 1 && Cout > 1), "MVS_FLAT2D: stride-1 layers with a C8 output only");
+    const LayerGeom g = make_geom(Cin, Cout, stride, transposed, flat2d);
+    MVS_REQUIRE(!flat2d || g.tmerged, "MVS_FLAT2D: this layer shape has no T-merged plan");
     MVS_REQUIRE((int)g.srcs.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
     PackPlan pp;
     memset(&pp, 0, sizeof(pp));
@@ -1439,6 +1546,7 @@ extern "C" int mvs_conv3d_c8_pack_weights_ex(const float *w, void *packed, int C
     pp.pad_rows = g.pad_rows;
     pp.grp_rows = g.tmerged ? g.row_cols : 0;
     pp.n_grp = g.n_grp;
+    pp.n_t = g.n_t;
     const long long total = (long long)g.cout_tiles * pp.n_ksteps * 2 * ((g.tmerged ? g.n_grp * g.row_cols : g.nblk * g.n) + g.pad_rows) * 8;
     pack_weights_kernel<<<cdiv(total, 256) > 1024 ? 1024 : cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         pp, w, (uint16_t *)packed, (flags & MVS_ACT_F16) ? 1 : 0);
@@ -1453,7 +1561,11 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "extents must be positive");
     MVS_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
     MVS_REQUIRE(x_c8 && w_packed && y, "null pointer");
-    const LayerGeom g = make_geom(Cin, Cout, stride, transposed);
+    const bool flat2d = (flags & MVS_FLAT2D) != 0;
+    MVS_REQUIRE(!flat2d || (D == 1 && stride == 1 && Cout > 1 && !skip_c8 && !(flags & (MVS_Y_DW | MVS_SKIP_DW))),
+                "MVS_FLAT2D: D = 1, stride 1, C8 output, no skip, natural W order");
+    const LayerGeom g = make_geom(Cin, Cout, stride, transposed, flat2d);
+    MVS_REQUIRE(!flat2d || g.tmerged, "MVS_FLAT2D: this layer shape has no T-merged plan");
     MVS_REQUIRE((int)g.srcs.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
     static thread_local ConvPlan P;
     size_t smem = 0;

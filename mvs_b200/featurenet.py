@@ -22,6 +22,7 @@ BASELINE.json's north_star keeps the 2D extractor in PyTorch; what is built here
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Sequence
 
 import torch
@@ -128,6 +129,12 @@ def _as_3x3x3(w2d: torch.Tensor) -> torch.Tensor:
     return w3
 
 
+# Layout of the native engine's maps: True = batch-major [N,CB,H,W,8] with the flat 2D mode of the convolution kernel
+# (MVS_FLAT2D: up to 15 image rows per pipeline step); False = full- / half-resolution maps folded onto the kernel's depth
+# axis ([CB,N,H,W,8], MVS_KD1: N rows per step) -- the round-2 form, kept for A/B runs (MVS_FEATURE_FLAT2D=0).
+FLAT2D = os.environ.get("MVS_FEATURE_FLAT2D", "1") != "0"
+
+
 class _NativeLayer:
     """Packed fp16 tcgen05 weights + folded-BN affine of one extractor layer, rebuilt when a parameter changes."""
 
@@ -142,6 +149,7 @@ class _NativeLayer:
             w3 = _as_3x3x3(self.conv.weight)
             self.cout, self.cin = w3.shape[0], w3.shape[1]
             self.packed = ops.pack_conv_weights(w3, 1, False, act_f16=True)
+            self.packed_flat = ops.pack_conv_weights(w3, 1, False, act_f16=True, flat2d=True)
             self.scale, self.shift = _bn_affine(self.bn)
             if self.conv.bias is not None:          # conv bias (no BN on such layers in the reference: it goes into the shift)
                 b = self.conv.bias.detach().float()
@@ -159,8 +167,12 @@ class _NativeLayer:
                               layout=_lib.KD1)
             return y.view(y.shape[1], N, H, W, 8)
         N, CB, H, W, _ = x.shape
-        y = ops.conv3d_c8(x.view(N, CB, 1, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu, act_f16=True,
-                              layout=_lib.KD1)
+        if FLAT2D:      # batch-major maps, one image per batch element: the kernel tiles the image rows (no depth axis)
+            y = ops.conv3d_c8(x.view(N, CB, 1, H, W, 8), L.packed_flat, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu,
+                              act_f16=True, layout=_lib.FLAT2D)
+        else:
+            y = ops.conv3d_c8(x.view(N, CB, 1, H, W, 8), L.packed, L.cin, L.cout, L.scale, L.shift, None, 1, False, self.relu,
+                              act_f16=True, layout=_lib.KD1)
         return y.view(N, y.shape[1], H, W, 8)
 
 
@@ -263,6 +275,15 @@ class FeatureNet(nn.Module):
         # The full- and half-resolution layers run FOLDED ([CB,N,H,W,8] = one volume with D = N images on the convolution's
         # row axis); maps with one channel block have the same bytes in both layouts, the builder's inputs are batch-major.
         N = x.shape[0]
+        if FLAT2D:
+            conv0 = L[1](L[0](ops.img_to_c8h(x)))                                          # [N,1,H,W,8]
+            conv1 = L[4](L[3](L[2](ops.s2d_c8(conv0))))                                    # [N,2,H/2,W/2,8]
+            conv2 = L[7](L[6](L[5](ops.s2d_c8(conv1))))                                    # [N,4,H/4,W/4,8]
+            out = {"stage1": nv["out1"](conv2)}
+            intra = ops.fpn_merge_c8h(conv1, w1, b1, conv2)
+            out["stage2"] = nv["out2"](intra)
+            out["stage3"] = nv["out3"](ops.fpn_merge_c8h(conv0, w2, b2, intra))
+            return out
         t = ops.img_to_c8h(x).view(1, N, *x.shape[2:], 8)         # [1,N,H,W,8]: CB = 1, folded == batch-major
         conv0 = L[1](L[0](t, True), True)                         # [1,N,H,W,8]
         conv1 = L[4](L[3](L[2](ops.s2d_c8(conv0, True, True), True), True), True)          # [2,N,H/2,W/2,8] folded

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import modules, ops
+from . import featurenet, modules, ops
 from .featurenet import _NativeLayer
 
 
@@ -57,6 +57,10 @@ class FeatureNet(nn.Module):
                                                                       self.conv5, self.conv6)] + [_NativeLayer(self.feature, None, False)]
         L = self._native
         N = x.shape[0]
+        if featurenet.FLAT2D:                                                    # batch-major maps, flat 2D convolution mode
+            c1 = L[1](L[0](ops.img_to_c8h(x)))
+            c4 = L[4](L[3](L[2](ops.s2d_c8(c1))))
+            return L[7](L[6](L[5](ops.s2d_c8(c4))))                              # C8H [N,4,h,w,8]
         t = ops.img_to_c8h(x).view(1, N, *x.shape[2:], 8)                       # CB = 1: folded == batch-major
         c1 = L[1](L[0](t, True), True)
         c4 = L[4](L[3](L[2](ops.s2d_c8(c1, True, True), True), True), True)      # [2,N,H/2,W/2,8] folded

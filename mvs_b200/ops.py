@@ -433,9 +433,11 @@ def cas_hypotheses(prev_depth, img_hw, stage_hw, ndepth: int, depth_interval_pix
 
 
 # ---- fast path: bf16 C8 convolution on the tcgen05 tensor cores -----------------------------------
-def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = False, act_f16: bool = False) -> torch.Tensor:
+def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = False, act_f16: bool = False,
+                      flat2d: bool = False) -> torch.Tensor:
     """fp32 [Cout,Cin,3,3,3] (or [Cin,Cout,3,3,3] when transposed) -> opaque packed bf16 (act_f16: fp16) blocks for
-    conv3d_c8 (uint8 tensor on the weight's device)."""
+    conv3d_c8 (uint8 tensor on the weight's device).  flat2d: blocks for conv3d_c8(..., layout=L.FLAT2D) -- only the centre
+    depth slice weight[:, :, 1] is used (a plain 2D convolution)."""
     weight = _f32c(weight.detach())
     _dev(weight)
     cin = weight.shape[0] if transposed else weight.shape[1]
@@ -446,7 +448,8 @@ def pack_conv_weights(weight: torch.Tensor, stride: int = 1, transposed: bool = 
     packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
     with torch.cuda.device(weight.device):
         check(lib().mvs_conv3d_c8_pack_weights_ex(_p(weight), _p(packed), cin, cout, stride, int(transposed),
-                                                  L.ACT_F16 if act_f16 else 0, _stream()), "mvs_conv3d_c8_pack_weights")
+                                                  (L.ACT_F16 if act_f16 else 0) | (L.FLAT2D if flat2d else 0), _stream()),
+              "mvs_conv3d_c8_pack_weights")
     return packed
 
 
