@@ -123,6 +123,8 @@ struct ConvPlan {
     // and the step axis walks the row blocks of the image.  The kh taps ride the row-tap groups, there are NO step taps: an
     // output step reads one buffer, one partial (n TMEM columns per row instead of 3 n -> up to 15 rows per step for n = 8).
     int flat2d;
+    int pair_store;                                 // transposed stride-2 layers with Cout <= 8: even / odd output columns of a row
+                                                    // leave as one 32-byte store (y 32-byte aligned, Wo even)
     int op_begin[UM_MAX_ISSUERS][4];                // issuer j, depth slab r: ops [op_begin[j][r], op_begin[j][r+1])
     AccOut acc[UM_MAX_ACC];
     // issue-ready op table (16 B per MMA, read with one uniform constant load):
@@ -917,8 +919,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
             // of the step's skip vectors before the tfull wait -- epilogue work 3.6 k -> 2.9 k clk per step but the CTA
             // slower, 5.1 k -> 6.5 k: the prefetch pass itself sits on this role's critical path; holding the first batch in
             // registers across the wait spills at 64 registers.)
-            auto store_with = [&](const uint32_t (&v)[8], uint32_t oidx, const uint4 &sk, const float2 (&scl)[4],
-                                  const float2 (&shl)[4]) {
+            auto pack_with = [&](const uint32_t (&v)[8], const uint4 &sk, const float2 (&scl)[4], const float2 (&shl)[4]) -> uint4 {
                 const uint32_t sv[4] = {sk.x, sk.y, sk.z, sk.w};
                 uint32_t pk[4];
 #pragma unroll
@@ -931,8 +932,10 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                     }
                     pk[e] = P.f16 ? pack_f16x2(t.x, t.y) : pack_bf16x2(t.x, t.y);
                 }
-                ybase[oidx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                return make_uint4(pk[0], pk[1], pk[2], pk[3]);
             };
+            auto store_with = [&](const uint32_t (&v)[8], uint32_t oidx, const uint4 &sk, const float2 (&scl)[4],
+                                  const float2 (&shl)[4]) { ybase[oidx] = pack_with(v, sk, scl, shl); };
             auto store_chunk = [&](const uint32_t (&v)[8], int nloc, uint32_t oidx, const uint4 &sk) {
                 float2 scl[4], shl[4];
 #pragma unroll
@@ -994,9 +997,22 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                         }
                     }
                     tmem_wait_ld();
+                    if (P.pair_store) {
+                        // transposed layers: accumulators 2k, 2k + 1 are the even / odd output columns of the same row --
+                        // one 32-byte store of the two neighbours instead of two 16-byte stores at a 32-byte stride
 #pragma unroll
-                    for (int j = 0; j < EB; ++j)
-                        if (ok[j]) store_with(r[j], pos[j], sk[j], sc2, sh2);
+                        for (int j = 0; j < EB; j += 2)
+                            if (ok[j]) {
+                                const uint4 v0 = pack_with(r[j], sk[j], sc2, sh2), v1 = pack_with(r[j + 1], sk[j + 1], sc2, sh2);
+                                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                             :: "l"(ybase + pos[j]), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w), "r"(v1.x), "r"(v1.y),
+                                                "r"(v1.z), "r"(v1.w) : "memory");
+                            }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < EB; ++j)
+                            if (ok[j]) store_with(r[j], pos[j], sk[j], sc2, sh2);
+                    }
                 }
             } else {
                 for (int a = eg; a < P.n_acc; a += NEG) {
@@ -1580,6 +1596,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     MVS_REQUIRE(!P.y_dw || (P.tmerged && !out_f32), "MVS_Y_DW: only the stride-1 C8 layers write a W-de-interleaved output");
     MVS_REQUIRE(!P.skip_dw || skip_c8, "MVS_SKIP_DW without a skip tensor");
     MVS_REQUIRE(!P.skip_dw || P.tmerged || g.mode == UM_DECONV_S2, "MVS_SKIP_DW: stride-1 and transposed stride-2 layers only");
+    P.pair_store = (g.mode == UM_DECONV_S2 && Cout <= 8 && !out_f32 && ((uintptr_t)y & 31) == 0 && P.n_acc % 2 == 0) ? 1 : 0;
     P.trace = g_trace; P.trace_ctas = g_trace_ctas;
     P.ring_magic = (1u << 18) / (uint32_t)P.ring + 1u;
     MVS_REQUIRE((long long)P.Do * P.Ho * P.Wo * (P.n >> 3 > 0 ? P.n >> 3 : 1) < (1ll << 31), "output volume too large for 32-bit tile offsets");
