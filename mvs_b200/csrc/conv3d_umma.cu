@@ -305,6 +305,9 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                    void *__restrict__ y)
 {
     constexpr bool kSkip = MC == 2;          // the launcher picks the <., 2> instantiations exactly when a skip tensor is given
+    // <true, 4> = the flat 2D mode (ConvPlan::flat2d): its own instantiation, so that the 3D T-merged kernels keep the code
+    // and the register allocation they were tuned with (as run-time branches the extra paths cost them 5-15 %)
+    constexpr bool kFlat = TM && MC == 4;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4 *sw = reinterpret_cast<uint4 *>(smem_raw);                 // packed weights of this Cout tile
     uint4 *sa = sw + P.weight_units + P.zero_units;                  // ring of depth slabs (after weights + zero block)
@@ -383,7 +386,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     tc_fence_after();
     const uint32_t taddr = *tmem_slot;
     if (trace && tid == 0) { trace[9] = clock64() - t_cta0; trace[10] = nsteps; }
-    const int n_slabs = TM ? (P.flat2d ? nsteps : nsteps + 2) : P.d_mul * (nsteps - 1) + P.rd;   // slabs this CTA stages in total
+    const int n_slabs = TM ? (kFlat ? nsteps : nsteps + 2) : P.d_mul * (nsteps - 1) + P.rd;   // slabs this CTA stages in total
 
     if (TM && (warp < 4 || warp >= 12)) {
         // =========================== T-merged epilogue: TMEM -> registers -> global =====================
@@ -399,8 +402,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         const int ow = m0 + m;
         // output index of (row a, step): pos0 + a * row_stride + step * step_stride  (hoisted 64-bit arithmetic)
         const size_t plane_o = (size_t)P.Hor * P.Wo;
-        const size_t row_stride = (P.swap && !P.flat2d) ? plane_o : (size_t)P.Wo;
-        const size_t step_stride = P.flat2d ? (size_t)P.ht * P.Wo : (P.swap ? (size_t)P.Wo : plane_o);
+        const size_t row_stride = (P.swap && !kFlat) ? plane_o : (size_t)P.Wo;
+        const size_t step_stride = kFlat ? (size_t)P.ht * P.Wo : (P.swap ? (size_t)P.Wo : plane_o);
         const size_t pos00 = (size_t)h0 * row_stride + (size_t)step_begin * step_stride;
         const size_t pos0 = pos00 + (size_t)ow;
         const bool w_ok = ow < P.Wo;
@@ -421,7 +424,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         }
         RoleTimer rt; rt.start(trace && tid == 0, trace, 6);
         for (int step = 0; step < nsteps; ++step) {
-            if (P.flat2d) {
+            if (kFlat) {
                 // ---- flat 2D: one slab, one partial per output row block ----
                 mbar_wait(tfull + (step & (UM_TBUFS - 1)), (uint32_t)(step >> UM_TBUFS_LOG2) & 1u);
                 rt.lap(6);
@@ -581,7 +584,7 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         // (Stride-2 layers over a W-de-interleaved input, x_dw: their cp.async lanes read contiguous 16 B vectors, 4 L1
         // wavefronts per instruction instead of 8.  One bulk copy per staged line was tried on top of that and is not
         // faster -- conv1 unchanged, the multi-chunk conv3 / conv5 10-25 % slower: 2-3 UBLKCP per lane and slab.)
-        if (TM && P.flat2d) {
+        if (kFlat) {
             // flat 2D: slab i = image rows (step_begin + i) * ht - 1 .. + ht of every channel block; one bulk copy per line,
             // rows above / below the image (first / last block) and the column halo are zero-filled
             RoleTimer rt; rt.start(trace && tid == 128, trace, 1);
@@ -1650,7 +1653,8 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
         return cudaSuccess;
     };
     cudaError_t e;
-    if (P.tmerged) e = skip_c8 ? launch(conv3d_umma_kernel<true, 2>, UM_THREADS_TM) : launch(conv3d_umma_kernel<true, 1>, UM_THREADS_TM);
+    if (P.tmerged && P.flat2d) e = launch(conv3d_umma_kernel<true, 4>, UM_THREADS_TM);
+    else if (P.tmerged) e = skip_c8 ? launch(conv3d_umma_kernel<true, 2>, UM_THREADS_TM) : launch(conv3d_umma_kernel<true, 1>, UM_THREADS_TM);
     else if (skip_c8) e = launch(conv3d_umma_kernel<false, 2>, UM_THREADS + UM_EPI_THREADS);
     else e = launch(conv3d_umma_kernel<false, 3>, UM_THREADS);
     if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
