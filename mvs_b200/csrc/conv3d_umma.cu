@@ -384,6 +384,12 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Programmatic dependent launch (the launcher sets the attribute): everything above -- TMEM allocation, barrier
+    // initialisation, weight staging, index tables -- reads nothing a preceding kernel writes, so it may run under the tail of
+    // the previous layer; from here on the activations are touched, so wait for the preceding grid to complete and flush.
+    // The next layer's CTAs may start their own prologue as soon as every CTA of this grid is past this point.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t taddr = *tmem_slot;
     if (trace && tid == 0) { trace[9] = clock64() - t_cta0; trace[10] = nsteps; }
     const int n_slabs = TM ? (kFlat ? nsteps : nsteps + 2) : P.d_mul * (nsteps - 1) + P.rd;   // slabs this CTA stages in total
@@ -1648,9 +1654,17 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     auto launch = [&](auto kernel, int threads) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(P, (const uint4 *)x_c8, (const uint4 *)w_packed, scale, shift,
-                                                              (const uint4 *)skip_c8, y);
-        return cudaSuccess;
+        // launched with programmatic stream serialization: the prologue of this layer overlaps the tail of the previous
+        // kernel in the stream (see griddepcontrol.wait in the kernel); MVS_PDL=0 switches it off (A/B knob)
+        static const bool pdl = !(getenv("MVS_PDL") && atoi(getenv("MVS_PDL")) == 0);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kernel, P, (const uint4 *)x_c8, (const uint4 *)w_packed, scale, shift,
+                                  (const uint4 *)skip_c8, y);
     };
     cudaError_t e;
     if (P.tmerged && P.flat2d) e = launch(conv3d_umma_kernel<true, 4>, UM_THREADS_TM);

@@ -16,6 +16,8 @@ namespace mvs {
 __global__ void __launch_bounds__(256)
 img_to_c8h_kernel(const void *__restrict__ img, int is_u8, uint4 *__restrict__ dst, long long plane)
 {
+    // (lets a dependent conv layer launched with programmatic stream serialization start its prologue under our tail)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= plane) return;
     const int n = blockIdx.y;
@@ -42,6 +44,8 @@ __device__ __forceinline__ size_t map_plane(int n, int cb, int N, int CB, bool f
 __global__ void __launch_bounds__(256)
 s2d_c8_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int N, int CB, int H, int W, int Ho, int Wo, int flags)
 {
+    // (lets a dependent conv layer launched with programmatic stream serialization start its prologue under our tail)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= Wo || y >= Ho) return;
     const int n = blockIdx.z / CB, cb = blockIdx.z % CB;
@@ -71,6 +75,8 @@ __global__ void __launch_bounds__(128)
 fpn_merge_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ prev, uint4 *__restrict__ out,
                  const __grid_constant__ Lateral L, int H, int W, int Hp, int Wp, int flags)
 {
+    // (lets a dependent conv layer launched with programmatic stream serialization start its prologue under our tail)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int px = blockIdx.x * 128 + threadIdx.x, py = blockIdx.y, n = blockIdx.z, N = gridDim.z;
     if (px >= W) return;
     const size_t plane = (size_t)H * W, pix = (size_t)py * W + px;

@@ -12,6 +12,8 @@ softargmin_conf_kernel(const float *__restrict__ logits, const float *__restrict
                        float *__restrict__ out_depth, float *__restrict__ out_conf, float *__restrict__ out_prob,
                        int32_t *__restrict__ out_index, int B, int D, long long plane, int clamp_index, int is_prob)
 {
+    // (lets a dependent conv layer launched with programmatic stream serialization start its prologue under our tail)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (i >= plane) return;
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(256)
 cas_hypotheses_kernel(const float *__restrict__ prev, int hp, int wp, int H, int W, int h, int w, int nd, float half,
                       float *__restrict__ out)
 {
+    // (lets a dependent conv layer launched with programmatic stream serialization start its prologue under our tail)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (x >= w) return;
     const float *pd = prev + (size_t)b * hp * wp;
