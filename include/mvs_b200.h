@@ -53,6 +53,8 @@ extern "C" {
                                   convolution over D stacked images; the kernel skips the other depth taps' MMAs            */
 #define MVS_FLAT2D 65536       /* conv3d_c8 + pack_weights_ex (stride 1, D = 1): plain 2D convolution with the centre depth slice of
                                   the weights; the kernel tiles the image rows instead of a depth axis (no step-tap partials)  */
+#define MVS_SKIP_PS 131072     /* conv3d_c8 + MVS_FLAT2D: the skip operand is a half-resolution map [N][4*Cout/8][H/2][W/2][8] whose block
+                                  ((h&1)*2 + (w&1)) * Cout/8 + cb holds the value for output pixel (h, w) ("pixel-shuffled")     */
 #define MVS_WARP_TMA 1024       /* C8 builder: force the TMA-staged kernel (fp16 maps only); neither bit: library picks */
 
 /* depth_mode */
@@ -150,6 +152,11 @@ int mvs_img_to_c8h(const void *img, int src_dtype, void *dst_c8h, int N, int H, 
 int mvs_s2d_c8(const void *src_c8, void *dst_c8, int N, int CB, int H, int W, int flags, void *stream);
 int mvs_fpn_merge_c8h(const void *x_c8h, const float *w_host, const float *bias_host, const void *prev_c8h,
                       void *out_c8h, int N, int Cin, int H, int W, int Hp, int Wp, int flags, void *stream);
+/* y[n, c, h, w] += corr[(rc * 3 + cc) * C + c] on the one-pixel border of fp16 C8 maps [N][C/8][H][W][8] (rc / cc = 0 first, 1
+ * inner, 2 last row / column; corr_host [9][C] is a HOST pointer, C <= 32).  Used when the last FPN stage is evaluated by
+ * linearity -- out3(up2(intra) + inner2(conv0)) as two convolutions (featurenet.py) -- for the lateral bias, which a zero-padded
+ * 3x3 convolution does not see outside the image (CasMVSNet/models/module.py:393-398). */
+int mvs_border_add_c8h(void *y_c8h, const float *corr_host, int N, int C, int H, int W, void *stream);
 
 /* ---- a3: 3x3x3 convolution + folded BatchNorm + ReLU + skip ------------------------------------
  * Replaces ConvBnReLU3D / Conv3d / Deconv3d blocks and the skip adds of CostRegNet.forward:

@@ -25,6 +25,7 @@ WARP_NO_TMA = 512
 WARP_TMA = 1024
 ACT_F16 = 2048
 X_DW, Y_DW, SKIP_DW = 4096, 8192, 16384      # conv3d_c8: W-de-interleaved input / output / skip tensor
+SKIP_PS = 131072                             # conv3d_c8 + FLAT2D: pixel-shuffled half-resolution skip operand
 FLAT2D = 65536                               # conv3d_c8 / pack: plain 2D convolution (D = 1), image rows tiled by the kernel
 KD1 = 32768                                  # conv3d_c8: weights zero outside the centre depth tap (stacked 2D images)
 DEPTH_PLANE = 0
@@ -55,6 +56,7 @@ SIGNATURES = {
     "mvs_img_to_c8h": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     "mvs_s2d_c8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mvs_fpn_merge_c8h": (_i, [_vp] * 5 + [_i] * 7 + [_vp]),
+    "mvs_border_add_c8h": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
     "mvs_conv3d_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
     "mvs_conv3d_wgrad": (_i, [_vp] * 3 + [_i] * 8 + [_vp]),
     "mvs_conv3d_c8_packed_weight_bytes": (_i64, [_i] * 4),

@@ -307,7 +307,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
     constexpr bool kSkip = MC == 2;          // the launcher picks the <., 2> instantiations exactly when a skip tensor is given
     // <true, 4> = the flat 2D mode (ConvPlan::flat2d): its own instantiation, so that the 3D T-merged kernels keep the code
     // and the register allocation they were tuned with (as run-time branches the extra paths cost them 5-15 %)
-    constexpr bool kFlat = TM && MC == 4;
+    constexpr bool kFlat = TM && (MC == 4 || MC == 5);
+    // <true, 5>: flat 2D + a "pixel-shuffled" skip operand (MVS_SKIP_PS): the value added to output pixel (h, w) of channel
+    // block cb sits in block ((h & 1) * 2 + (w & 1)) * cout_chunks + cb of a HALF-resolution map [N][4 * cout_chunks][H/2][W/2][8]
+    // -- a convolution of a nearest-up-sampled map, computed at the low resolution as four parity classes (featurenet.py)
+    constexpr bool kFlatSkip = TM && MC == 5;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4 *sw = reinterpret_cast<uint4 *>(smem_raw);                 // packed weights of this Cout tile
     uint4 *sa = sw + P.weight_units + P.zero_units;                  // ring of depth slabs (after weights + zero block)
@@ -440,10 +444,22 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                 const int row_lim = P.Hr - (step_begin + step) * P.ht;            // image rows left in this block
                 for (int it = 0; it < n_items; it += 4) {
                     uint32_t q[4][8];
+                    uint4 sk[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (it + j < n_items)
-                            tmem_ld8_nowait(tc + (uint32_t)((eg + 2 * ((it + j) >> nb_shift)) * n3 + ((it + j) & (nb - 1)) * 8), q[j]);
+                        if (it + j < n_items) {
+                            const int a = eg + 2 * ((it + j) >> nb_shift), n0 = ((it + j) & (nb - 1)) * 8;
+                            if (kFlatSkip) {
+                                sk[j] = make_uint4(0, 0, 0, 0);
+                                const int h = (step_begin + step) * P.ht + a, cb = ct * nb + (n0 >> 3);
+                                if (w_ok && a < row_lim && cb < P.cout_chunks) {
+                                    const int hh = P.Hr >> 1, wh = P.W >> 1;
+                                    const size_t blk = (size_t)b * 4 * P.cout_chunks + (size_t)(((h & 1) * 2 + (ow & 1)) * P.cout_chunks + cb);
+                                    sk[j] = __ldg(skip + (blk * hh + (h >> 1)) * wh + (ow >> 1));
+                                }
+                            }
+                            tmem_ld8_nowait(tc + (uint32_t)(a * n3 + n0), q[j]);
+                        }
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -457,6 +473,11 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                                                   make_float2(s_scale[n0 + 2 * e], s_scale[n0 + 2 * e + 1]),
                                                   make_float2(s_shift[n0 + 2 * e], s_shift[n0 + 2 * e + 1]));
                             if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                            if (kFlatSkip) {
+                                const uint32_t sv = e == 0 ? sk[j].x : (e == 1 ? sk[j].y : (e == 2 ? sk[j].z : sk[j].w));
+                                if (P.f16) { const float2 s2 = unpack_f16x2(sv); v.x += s2.x; v.y += s2.y; }
+                                else { v.x += __uint_as_float(sv << 16); v.y += __uint_as_float(sv & 0xffff0000u); }
+                            }
                             pk[e] = P.f16 ? pack_f16x2(v.x, v.y) : pack_bf16x2(v.x, v.y);
                         }
                         ybase[so + (uint32_t)a * rs32 + (uint32_t)(n0 >> 3) * vo32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1587,8 +1608,11 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
     MVS_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
     MVS_REQUIRE(x_c8 && w_packed && y, "null pointer");
     const bool flat2d = (flags & MVS_FLAT2D) != 0;
-    MVS_REQUIRE(!flat2d || (D == 1 && stride == 1 && Cout > 1 && !skip_c8 && !(flags & (MVS_Y_DW | MVS_SKIP_DW))),
-                "MVS_FLAT2D: D = 1, stride 1, C8 output, no skip, natural W order");
+    const bool skip_ps = (flags & MVS_SKIP_PS) != 0;
+    MVS_REQUIRE(!flat2d || (D == 1 && stride == 1 && Cout > 1 && (!skip_c8 || skip_ps) && !(flags & (MVS_Y_DW | MVS_SKIP_DW))),
+                "MVS_FLAT2D: D = 1, stride 1, C8 output, natural W order; a skip operand only as MVS_SKIP_PS");
+    MVS_REQUIRE(!skip_ps || (flat2d && skip_c8 && H % 2 == 0 && W % 2 == 0),
+                "MVS_SKIP_PS: flat 2D layers with a skip operand and even H, W only");
     const LayerGeom g = make_geom(Cin, Cout, stride, transposed, flat2d);
     MVS_REQUIRE(!flat2d || g.tmerged, "MVS_FLAT2D: this layer shape has no T-merged plan");
     MVS_REQUIRE((int)g.srcs.size() <= UM_MAX_KSTEPS, "too many k-steps for this layer (Cin too large)");
@@ -1667,7 +1691,7 @@ extern "C" int mvs_conv3d_c8_fwd(const void *x_c8, const void *w_packed, const f
                                   (const uint4 *)skip_c8, y);
     };
     cudaError_t e;
-    if (P.tmerged && P.flat2d) e = launch(conv3d_umma_kernel<true, 4>, UM_THREADS_TM);
+    if (P.tmerged && P.flat2d) e = skip_c8 ? launch(conv3d_umma_kernel<true, 5>, UM_THREADS_TM) : launch(conv3d_umma_kernel<true, 4>, UM_THREADS_TM);
     else if (P.tmerged) e = skip_c8 ? launch(conv3d_umma_kernel<true, 2>, UM_THREADS_TM) : launch(conv3d_umma_kernel<true, 1>, UM_THREADS_TM);
     else if (skip_c8) e = launch(conv3d_umma_kernel<false, 2>, UM_THREADS + UM_EPI_THREADS);
     else e = launch(conv3d_umma_kernel<false, 3>, UM_THREADS);

@@ -9,6 +9,8 @@
 //                       out = nearest_up2(prev) + conv1x1(x) + bias   -- 32 channels out, never materialising the up-sampled
 //                       map or the lateral map; weights sit in the constant bank (kernel parameter), fp32 math
 // All HBM-bound, one 16-byte vector per lane per channel block, fully coalesced.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace mvs {
@@ -108,9 +110,48 @@ fpn_merge_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ prev, ui
     }
 }
 
+struct BorderCorr {        // per-channel additive terms of the 8 border classes (row class * 3 + column class; centre unused)
+    float c[9][32];
+};
+
+// y[n, :, h, w] += corr[rc(h) * 3 + cc(w)] on the one-pixel border of fp16 C8 maps [N][CB][H][W][8] (rc: 0 top, 1 inner, 2 bottom)
+__global__ void __launch_bounds__(128)
+border_add_c8h_kernel(uint4 *__restrict__ y, const __grid_constant__ BorderCorr B, int CB, int H, int W)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int per = 2 * W + 2 * (H - 2);                       // perimeter pixels: top row, bottom row, left / right columns
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= per) return;
+    int h, w;
+    if (i < W) { h = 0; w = i; }
+    else if (i < 2 * W) { h = H - 1; w = i - W; }
+    else { const int k = i - 2 * W; h = 1 + (k >> 1); w = (k & 1) ? W - 1 : 0; }
+    const int cls = (h == 0 ? 0 : (h == H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == W - 1 ? 2 : 1));
+    const int cb = blockIdx.y, n = blockIdx.z;
+    uint4 *p = y + (((size_t)n * CB + cb) * H + h) * W + w;
+    const uint4 v = *p;
+    const float2 a = h2f(v.x), b = h2f(v.y), c = h2f(v.z), d = h2f(v.w);
+    const float *k = &B.c[cls][cb * 8];
+    *p = make_uint4(f2h(a.x + k[0], a.y + k[1]), f2h(b.x + k[2], b.y + k[3]), f2h(c.x + k[4], c.y + k[5]), f2h(d.x + k[6], d.y + k[7]));
+}
+
 }  // namespace mvs
 
 using namespace mvs;
+
+extern "C" int mvs_border_add_c8h(void *y_c8h, const float *corr_host, int N, int C, int H, int W, void *stream)
+{
+    if (N == 0 || H == 0 || W == 0) return MVS_OK;
+    MVS_REQUIRE(y_c8h && corr_host, "null pointer");
+    MVS_REQUIRE(N > 0 && N <= 65535 && C > 0 && C <= 32 && C % 8 == 0 && H >= 2 && W >= 2, "bad extents (C <= 32, H, W >= 2)");
+    BorderCorr B;
+    memset(&B, 0, sizeof(B));
+    for (int k = 0; k < 9; ++k)
+        for (int c = 0; c < C; ++c) B.c[k][c] = corr_host[k * C + c];
+    const int per = 2 * W + 2 * (H - 2);
+    border_add_c8h_kernel<<<dim3(cdiv(per, 128), C / 8, N), 128, 0, (cudaStream_t)stream>>>((uint4 *)y_c8h, B, C / 8, H, W);
+    return check_launch("mvs_border_add_c8h");
+}
 
 extern "C" int mvs_img_to_c8h(const void *img, int src_dtype, void *dst_c8h, int N, int H, int W, void *stream)
 {

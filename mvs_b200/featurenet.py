@@ -129,10 +129,78 @@ def _as_3x3x3(w2d: torch.Tensor) -> torch.Tensor:
     return w3
 
 
+class _FusedOut3:
+    """The last FPN stage by linearity.  The reference computes (CasMVSNet/models/module.py:396-398)
+
+        out3(up2(intra) + inner2(conv0))        up2 = nearest x2, inner2 = 1x1 conv 8 -> 32 (+ bias), out3 = 3x3 conv 32 -> 8
+
+    through a 32-channel full-resolution map (600 MB written and re-read at 5 x 1600 x 1184).  Equivalent, without that map:
+      A   = conv3x3(intra; Wc)  at HALF resolution, 32 -> 4 x 8: output pixel (2y + py, 2x + px) of out3(up2(intra)) only sees
+            intra rows {y-1, y} (py = 0) or {y, y+1} (py = 1), likewise columns -- one 3x3 half-resolution kernel per parity class
+            (py, px), its taps the sums of the out3 taps that fall on the same intra pixel;
+      out = conv3x3(conv0; W') + shift' + A[class(h, w)][h/2][w/2]     with W' = out3 o inner2 composed (8 -> 8), the lateral bias
+            pushed through out3 into shift' -- and taken out again on the image border, where the zero padding of out3 hides it.
+    Weights are composed in float64 on the host and cached until a parameter changes."""
+
+    def __init__(self, out3: nn.Conv2d, inner2: nn.Conv2d):
+        self.out3, self.inner2, self.key = out3, inner2, None
+
+    def get(self):
+        ts = [self.out3.weight, self.inner2.weight] + [t for t in (self.out3.bias, self.inner2.bias) if t is not None]
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if key == self.key:
+            return self
+        dev = self.out3.weight.device
+        W3 = self.out3.weight.detach().double().cpu()                       # [Co, 32, 3, 3]
+        W2 = self.inner2.weight.detach().double().cpu()[:, :, 0, 0]         # [32, Ci]
+        co, cm = W3.shape[:2]
+        ci = W2.shape[1]
+        b2 = self.inner2.bias.detach().double().cpu() if self.inner2.bias is not None else torch.zeros(cm, dtype=torch.float64)
+        b3 = self.out3.bias.detach().double().cpu() if self.out3.bias is not None else torch.zeros(co, dtype=torch.float64)
+        # parity-class kernels over the half-resolution map: full-resolution tap k of class p lands on half-resolution offset
+        # floor((p + k - 1) / 2)  (p = 0: k = 0 -> -1, k = 1, 2 -> 0;  p = 1: k = 0, 1 -> 0, k = 2 -> +1)
+        Wc = torch.zeros(4 * co, cm, 3, 3, dtype=torch.float64)
+        for py in range(2):
+            for px in range(2):
+                for ky in range(3):
+                    for kx in range(3):
+                        r, c = (py + ky - 1) // 2 + 1, (px + kx - 1) // 2 + 1
+                        Wc[(py * 2 + px) * co:(py * 2 + px + 1) * co, :, r, c] += W3[:, :, ky, kx]
+        Wp = torch.einsum("omhw,mc->ochw", W3, W2)                          # out3 o inner2
+        tapb = torch.einsum("omhw,m->ohw", W3, b2)                          # the lateral bias seen through each out3 tap
+        corr = torch.zeros(9, co, dtype=torch.float64)
+        for rc in range(3):
+            for cc in range(3):
+                for ky in range(3):
+                    for kx in range(3):
+                        if (rc == 0 and ky == 0) or (rc == 2 and ky == 2) or (cc == 0 and kx == 0) or (cc == 2 and kx == 2):
+                            corr[rc * 3 + cc] -= tapb[:, ky, kx]
+        w3d = torch.zeros(4 * co, cm, 3, 3, 3); w3d[:, :, 1] = Wc.float()
+        self.packed_a = ops.pack_conv_weights(w3d.to(dev), 1, False, act_f16=True, flat2d=True)
+        w3d = torch.zeros(co, (ci + 7) // 8 * 8, 3, 3, 3); w3d[:, :ci, 1] = Wp.float()
+        self.packed_b = ops.pack_conv_weights(w3d.to(dev), 1, False, act_f16=True, flat2d=True)
+        self.shift = (b3 + tapb.sum(dim=(1, 2))).float().to(dev).contiguous()
+        self.corr = corr.float().contiguous()
+        self.co, self.cm, self.ci, self.key = co, cm, (ci + 7) // 8 * 8, key
+        return self
+
+    def __call__(self, conv0, intra):
+        """conv0 [N,Ci/8,H,W,8], intra [N,Cm/8,H/2,W/2,8] (fp16 C8) -> [N,Co/8,H,W,8]."""
+        F3 = self.get()
+        N, _, H, W, _ = conv0.shape
+        Hh, Wh = intra.shape[2:4]
+        a = ops.conv3d_c8(intra.view(N, F3.cm // 8, 1, Hh, Wh, 8), F3.packed_a, F3.cm, 4 * F3.co, None, None, None, 1, False, False,
+                          act_f16=True, layout=_lib.FLAT2D)
+        y = ops.conv3d_c8(conv0.view(N, F3.ci // 8, 1, H, W, 8), F3.packed_b, F3.ci, F3.co, None, F3.shift, a, 1, False, False,
+                          act_f16=True, layout=_lib.FLAT2D | _lib.SKIP_PS).view(N, -1, H, W, 8)
+        return ops.border_add_c8h(y, F3.corr)
+
+
 # Layout of the native engine's maps: True = batch-major [N,CB,H,W,8] with the flat 2D mode of the convolution kernel
 # (MVS_FLAT2D: up to 15 image rows per pipeline step); False = full- / half-resolution maps folded onto the kernel's depth
 # axis ([CB,N,H,W,8], MVS_KD1: N rows per step) -- the round-2 form, kept for A/B runs (MVS_FEATURE_FLAT2D=0).
 FLAT2D = os.environ.get("MVS_FEATURE_FLAT2D", "1") != "0"
+FUSED_OUT3 = os.environ.get("MVS_FEATURE_FUSED_OUT3", "1") != "0"      # the last FPN stage by linearity (_FusedOut3); A/B knob
 
 
 class _NativeLayer:
@@ -282,7 +350,13 @@ class FeatureNet(nn.Module):
             out = {"stage1": nv["out1"](conv2)}
             intra = ops.fpn_merge_c8h(conv1, w1, b1, conv2)
             out["stage2"] = nv["out2"](intra)
-            out["stage3"] = nv["out3"](ops.fpn_merge_c8h(conv0, w2, b2, intra))
+            H, W = conv0.shape[2:4]
+            if FUSED_OUT3 and H % 2 == 0 and W % 2 == 0 and H >= 2 and W >= 2 and tuple(intra.shape[2:4]) == (H // 2, W // 2):
+                if "fused3" not in nv:
+                    nv["fused3"] = _FusedOut3(self.out3, self.inner2)
+                out["stage3"] = nv["fused3"](conv0, intra)                                 # never builds the 32-channel map
+            else:
+                out["stage3"] = nv["out3"](ops.fpn_merge_c8h(conv0, w2, b2, intra))
             return out
         t = ops.img_to_c8h(x).view(1, N, *x.shape[2:], 8)         # [1,N,H,W,8]: CB = 1, folded == batch-major
         conv0 = L[1](L[0](t, True), True)                         # [1,N,H,W,8]

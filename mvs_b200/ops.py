@@ -477,7 +477,11 @@ def conv3d_c8(x_c8, packed_w, cin: int, cout: int, scale=None, shift=None, skip_
         y = torch.empty((B, 1, Do, Ho, Wo), dtype=torch.float32, device=x_c8.device)
     else:
         y = torch.empty((B, (cout + 7) // 8, Do, Ho, Wo, 8), dtype=adt, device=x_c8.device)
-    if skip_c8 is not None and (skip_c8.shape != y.shape or skip_c8.dtype != adt or not skip_c8.is_contiguous()):
+    if skip_c8 is not None and (int(layout) & L.SKIP_PS):
+        want = (B, 4 * ((cout + 7) // 8), Do, Ho // 2, Wo // 2, 8)       # pixel-shuffled half-resolution operand (flat 2D layers)
+        if tuple(skip_c8.shape) != want or skip_c8.dtype != adt or not skip_c8.is_contiguous() or Ho % 2 or Wo % 2:
+            raise ValueError(f"SKIP_PS: skip_c8 must be a contiguous C8 tensor {want} of the output's dtype (even H, W)")
+    elif skip_c8 is not None and (skip_c8.shape != y.shape or skip_c8.dtype != adt or not skip_c8.is_contiguous()):
         raise ValueError("skip_c8 must be a contiguous C8 tensor of the output's shape and dtype")
     with torch.cuda.device(x_c8.device):
         check(lib().mvs_conv3d_c8_fwd(_p(x_c8), _p(packed_w), _p(scale), _p(shift), _p(skip_c8), _p(y), B, cin, cout, D,
@@ -500,6 +504,19 @@ def img_to_c8h(imgs: torch.Tensor) -> torch.Tensor:
         check(lib().mvs_img_to_c8h(_p(imgs), L.U8 if imgs.dtype == torch.uint8 else L.F32, _p(out), N, H, W, _stream()),
               "mvs_img_to_c8h")
     return out
+
+
+def border_add_c8h(y: torch.Tensor, corr_host: torch.Tensor) -> torch.Tensor:
+    """In place: y[n, c, h, w] += corr[rc * 3 + cc, c] on the one-pixel border of an fp16 C8 map [N,C/8,H,W,8] (rc / cc: 0 first,
+    1 inner, 2 last row / column).  corr_host: float32 CPU tensor [9, C] (kernel-parameter operand)."""
+    _dev(y)
+    N, CB, H, W = _map_dims(y, False)
+    if y.dtype != torch.float16:
+        raise ValueError("y must be an fp16 C8 map")
+    corr = corr_host.detach().to("cpu", torch.float32).reshape(9, CB * 8).contiguous()
+    with torch.cuda.device(y.device):
+        check(lib().mvs_border_add_c8h(_p(y), _p(corr), N, CB * 8, H, W, _stream()), "mvs_border_add_c8h")
+    return y
 
 
 def _map_dims(x, folded):

@@ -61,6 +61,32 @@ def test_featurenet_mirror_strict_and_fast_vs_reference_golden():
             assert torch.equal(back, fast[k])
 
 
+@pytest.mark.parametrize("hw", [(48, 80), (8, 8), (36, 136), (4, 260)])
+def test_featurenet_last_stage_by_linearity(hw, monkeypatch):
+    """_FusedOut3 (out3(up2(intra) + inner2(conv0)) as two convolutions + a border term) against the plain sequence on the same
+    engine, and against the reference op sequence in fp32: both forms see the same fp16 conv0 / intra maps."""
+    from mvs_b200 import featurenet as FN
+    from oracle import torch_port as TP
+    H, W = hw
+    img = cu(cases.synth.images_u8(3, H, W, seed=5)[0])
+    net = FN.FeatureNet(mode="fast").to(DEV).eval()
+    net.load_state_dict(_sd(cases.featurenet_state(34)), strict=True)
+    with torch.no_grad():
+        monkeypatch.setattr(FN, "FUSED_OUT3", True)
+        fused = net(img)["stage3"].float()
+        monkeypatch.setattr(FN, "FUSED_OUT3", False)
+        plain = net(img)["stage3"].float()
+        ref = TP.featurenet(img.float() / 255.0, {k: v for k, v in net.state_dict().items()}, "")["stage3"]
+    scale = ref.abs().max().item()
+    e_fused, e_plain = (fused - ref).abs().max().item() / scale, (plain - ref).abs().max().item() / scale
+    print("stage3", hw, "fused", e_fused, "plain", e_plain, "fused vs plain", (fused - plain).abs().max().item() / scale)
+    assert (fused - plain).abs().max().item() <= 3e-3 * scale
+    assert e_fused <= max(1.5 * e_plain, 2e-3)
+    # the border is where the forms differ structurally: check it on its own
+    b = torch.ones_like(ref, dtype=torch.bool); b[..., 1:-1, 1:-1] = False
+    assert (fused - ref)[b].abs().max().item() <= max(1.5 * (plain - ref)[b].abs().max().item(), 2e-3 * scale)
+
+
 @pytest.mark.parametrize("cin,cout,H,W", [(8, 8, 21, 150), (32, 16, 12, 70), (64, 32, 9, 40), (32, 8, 16, 133), (16, 16, 7, 64)])
 def test_conv2d_on_the_tcgen05_kernel_fp16(cin, cout, H, W):
     """The extractor's 3x3 layers: mvs_conv3d_c8_fwd with D = 1 and MVS_ACT_F16 vs torch conv2d on fp16-rounded operands."""
