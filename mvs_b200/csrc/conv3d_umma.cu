@@ -436,30 +436,38 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
         for (int step = 0; step < nsteps; ++step) {
             if (kFlat) {
                 // ---- flat 2D: one slab, one partial per output row block ----
+                const int row_lim = P.Hr - (step_begin + step) * P.ht;            // image rows left in this block
+                // the skip vectors do not depend on the accumulators: all of this step's are requested BEFORE waiting for the
+                // MMAs (at most eight work items per thread: ht * n <= 120 columns per buffer, two epilogue groups)
+                uint4 sk[8];
+                if (kFlatSkip) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        sk[j] = make_uint4(0, 0, 0, 0);
+                        if (j < n_items) {
+                            const int a = eg + 2 * (j >> nb_shift), n0 = (j & (nb - 1)) * 8;
+                            const int h = (step_begin + step) * P.ht + a, cb = ct * nb + (n0 >> 3);
+                            if (w_ok && a < row_lim && cb < P.cout_chunks) {
+                                const int hh = P.Hr >> 1, wh = P.W >> 1;
+                                const size_t blk = (size_t)b * 4 * P.cout_chunks + (size_t)(((h & 1) * 2 + (ow & 1)) * P.cout_chunks + cb);
+                                sk[j] = __ldg(skip + (blk * hh + (h >> 1)) * wh + (ow >> 1));
+                            }
+                        }
+                    }
+                }
                 mbar_wait(tfull + (step & (UM_TBUFS - 1)), (uint32_t)(step >> UM_TBUFS_LOG2) & 1u);
                 rt.lap(6);
                 tc_fence_after();
                 const uint32_t tc = lane_base + (uint32_t)((step & (UM_TBUFS - 1)) * P.buf_cols);
                 const uint32_t so = (uint32_t)step * ss32;
-                const int row_lim = P.Hr - (step_begin + step) * P.ht;            // image rows left in this block
-                for (int it = 0; it < n_items; it += 4) {
+#pragma unroll
+                for (int it = 0; it < 8; it += 4) {
+                    if (it >= n_items) break;
                     uint32_t q[4][8];
-                    uint4 sk[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (it + j < n_items) {
-                            const int a = eg + 2 * ((it + j) >> nb_shift), n0 = ((it + j) & (nb - 1)) * 8;
-                            if (kFlatSkip) {
-                                sk[j] = make_uint4(0, 0, 0, 0);
-                                const int h = (step_begin + step) * P.ht + a, cb = ct * nb + (n0 >> 3);
-                                if (w_ok && a < row_lim && cb < P.cout_chunks) {
-                                    const int hh = P.Hr >> 1, wh = P.W >> 1;
-                                    const size_t blk = (size_t)b * 4 * P.cout_chunks + (size_t)(((h & 1) * 2 + (ow & 1)) * P.cout_chunks + cb);
-                                    sk[j] = __ldg(skip + (blk * hh + (h >> 1)) * wh + (ow >> 1));
-                                }
-                            }
-                            tmem_ld8_nowait(tc + (uint32_t)(a * n3 + n0), q[j]);
-                        }
+                        if (it + j < n_items)
+                            tmem_ld8_nowait(tc + (uint32_t)((eg + 2 * ((it + j) >> nb_shift)) * n3 + ((it + j) & (nb - 1)) * 8), q[j]);
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -474,7 +482,8 @@ conv3d_umma_kernel(const __grid_constant__ ConvPlan P, const uint4 *__restrict__
                                                   make_float2(s_shift[n0 + 2 * e], s_shift[n0 + 2 * e + 1]));
                             if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
                             if (kFlatSkip) {
-                                const uint32_t sv = e == 0 ? sk[j].x : (e == 1 ? sk[j].y : (e == 2 ? sk[j].z : sk[j].w));
+                                const uint4 &s4 = sk[it + j];
+                                const uint32_t sv = e == 0 ? s4.x : (e == 1 ? s4.y : (e == 2 ? s4.z : s4.w));
                                 if (P.f16) { const float2 s2 = unpack_f16x2(sv); v.x += s2.x; v.y += s2.y; }
                                 else { v.x += __uint_as_float(sv << 16); v.y += __uint_as_float(sv & 0xffff0000u); }
                             }
@@ -1320,6 +1329,7 @@ static bool build_plan(ConvPlan &P, const LayerGeom &g, int B, int Cin, int Cout
             if (ht > rows_ext && ht > 1) continue;
             const int buf_cols = round_up(ht * n3 + g.pad_rows, 16);
             if (UM_TBUFS * buf_cols > 512 || buf_cols > 256) continue;
+            if (flat2d && ((ht + 1) / 2) * (g.n >> 3) > 8) continue;     // the flat epilogue keeps at most eight work items per thread
             if ((pair_rows ? 2 : (int)g.ks.size()) * (ht + 2) + 1 > UM_MAX_OPS) continue;
             int ring = 0;
             for (int r = UM_MAX_RING; r >= 2 && !ring; r -= 2)          // even: see the issuer role
