@@ -33,6 +33,30 @@ img_to_c8h_kernel(const void *__restrict__ img, int is_u8, uint4 *__restrict__ d
     dst[(size_t)n * plane + i] = make_uint4(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b), 0u, 0u);
 }
 
+// uint8 images whose planes are 4-byte aligned: four pixels per thread (one 32-bit load per colour plane) and the 256 possible
+// quotients v / 255 -- the same correctly rounded fp32 division as above -- from a shared-memory table instead of 12 divisions
+__global__ void __launch_bounds__(256)
+img_u8x4_to_c8h_kernel(const uint32_t *__restrict__ img, uint4 *__restrict__ dst, long long plane4)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ float lut[256];
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= plane4) return;
+    const int n = blockIdx.y;
+    uint32_t v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = __ldg(img + ((size_t)n * 3 + k) * plane4 + i);
+    uint4 *o = dst + ((size_t)n * plane4 + i) * 4;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const __half2 a = __floats2half2_rn(lut[(v[0] >> (8 * p)) & 255u], lut[(v[1] >> (8 * p)) & 255u]);
+        const __half2 b = __floats2half2_rn(lut[(v[2] >> (8 * p)) & 255u], 0.f);
+        o[p] = make_uint4(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b), 0u, 0u);
+    }
+}
+
 // Map layouts: "batch-major" [N][CB][H][W][8] (what the builder takes, one contiguous map per view) or "folded"
 // [CB][N][H][W][8] -- the SAME bytes the tcgen05 convolution reads as ONE volume [B=1][CB][D=N][H][W][8], so that the N images
 // of a reference view ride the kernel's row axis (3D weights populated in the kd = 1 slice only: no mixing between images)
@@ -160,7 +184,10 @@ extern "C" int mvs_img_to_c8h(const void *img, int src_dtype, void *dst_c8h, int
     MVS_REQUIRE(img && dst_c8h, "null pointer");
     MVS_REQUIRE(src_dtype == MVS_F32 || src_dtype == MVS_U8, "images must be float32 or uint8");
     const long long plane = (long long)H * W;
-    img_to_c8h_kernel<<<dim3(cdiv(plane, 256), N), 256, 0, (cudaStream_t)stream>>>(img, src_dtype == MVS_U8, (uint4 *)dst_c8h, plane);
+    if (src_dtype == MVS_U8 && plane % 4 == 0 && ((uintptr_t)img & 3) == 0)
+        img_u8x4_to_c8h_kernel<<<dim3(cdiv(plane / 4, 256), N), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)img, (uint4 *)dst_c8h, plane / 4);
+    else
+        img_to_c8h_kernel<<<dim3(cdiv(plane, 256), N), 256, 0, (cudaStream_t)stream>>>(img, src_dtype == MVS_U8, (uint4 *)dst_c8h, plane);
     return check_launch("mvs_img_to_c8h");
 }
 

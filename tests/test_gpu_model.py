@@ -132,9 +132,13 @@ def test_s2d_and_fpn_merge_kernels():
     pf = ops.pack_c8(prev.float().to(DEV), torch.float16).permute(1, 0, 2, 3, 4).contiguous()
     of = ops.fpn_merge_c8h(xf, w, b, pf, x_folded=True, out_folded=True, prev_folded=True)
     assert torch.equal(of.permute(1, 0, 2, 3, 4), out)
-    u8 = torch.randint(0, 256, (2, 3, 9, 17), dtype=torch.uint8, generator=g)
-    c = ops.img_to_c8h(u8.to(DEV)).cpu()
-    assert torch.equal(c[:, 0, :, :, :3].permute(0, 3, 1, 2), (u8.float() / 255.0).half()) and not c[..., 3:].any()
+    for shape in ((2, 3, 9, 17), (3, 3, 12, 20), (1, 3, 256, 4)):      # odd plane: scalar kernel; plane % 4 == 0: four pixels per thread
+        u8 = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+        c = ops.img_to_c8h(u8.to(DEV)).cpu()
+        assert torch.equal(c[:, 0, :, :, :3].permute(0, 3, 1, 2), (u8.float() / 255.0).half()) and not c[..., 3:].any()
+    allv = torch.arange(256, dtype=torch.uint8).view(1, 1, 16, 16).expand(1, 3, 16, 16).contiguous()   # every byte value: the table
+    c = ops.img_to_c8h(allv.to(DEV)).cpu()
+    assert torch.equal(c[0, 0, :, :, 0].reshape(-1), (torch.arange(256).float() / 255.0).half())
 
 
 @pytest.mark.parametrize("mode", ["strict", "fast"])

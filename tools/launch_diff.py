@@ -20,7 +20,7 @@ def load(path):
     hdr, rows = rows[0], rows[1:]
     k, g, v = hdr.index("Kernel Name"), hdr.index("Grid Size"), hdr.index("Metric Value")
     launches = [(short(r[k]), r[g], float(r[v]) / 1e3) for r in rows]
-    starts = [i for i, l in enumerate(launches) if "img_to_c8h" in l[0]]
+    starts = [i for i, l in enumerate(launches) if "to_c8h_kernel" in l[0]]
     return launches[starts[-1]:]                      # the last whole-model step (earlier ones are warm-up)
 
 
