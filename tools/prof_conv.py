@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from mvs_b200 import synth, ops
+from mvs_b200 import synth, ops, _lib as L
 
 LAYERS = [  # name, cin(x base), cout, stride, transposed, input level, skip
     ("conv0", None, 1, 1, False, 0, False), ("conv1", 1, 2, 2, False, 0, False), ("conv2", 2, 2, 1, False, 1, False),
@@ -45,7 +45,10 @@ def main():
             wt = torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3), device=dev) / (27 * cin) ** 0.5
             pk = ops.pack_conv_weights(wt, stride, tr)
             scale = torch.ones(cout, device=dev); shift = torch.zeros(cout, device=dev)
-            fn = lambda skip=None: ops.conv3d_c8(x, pk, cin, cout, scale, shift, skip, stride, tr, cout != 1)
+            # layout flags as CostRegNet's fast path sets them (W-de-interleaved skip tensors)
+            lay0 = (L.X_DW if (stride == 2 and not tr) else 0) | (L.Y_DW if name in ("conv0", "conv2", "conv4") else 0)
+            fn = lambda skip=None: ops.conv3d_c8(x, pk, cin, cout, scale, shift, skip, stride, tr, cout != 1,
+                                                 layout=lay0 | (L.SKIP_DW if skip is not None else 0))
             y = fn()
             skip = torch.zeros_like(y) if has_skip else None
             for _ in range(2):
