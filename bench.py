@@ -393,8 +393,40 @@ def main_ours(args, wl):
         for _ in range(2):
             g_hot()
         ms = timed(g_hot, args.steps)
+        value_forms = {"serial": ms}
+        # Second launch form: consecutive reference views are independent, so two captured steps alternate on two streams and
+        # view i+1 fills the SMs that the low-resolution layers / kernel tails of view i leave idle.  Same kernels, same
+        # results, every step still a whole reference-view batch; the better form is reported (`value_form`).
+        g_hot_b = GraphedStep(hot_step)
+        vs = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        graphs, ev_done, vcount = [g_hot, g_hot_b], [torch.cuda.Event(), torch.cuda.Event()], [0]
+        ev_start = torch.cuda.Event()
+
+        def step_2s():
+            i = vcount[0]; vcount[0] += 1
+            j = i & 1
+            if i < 2:                                        # the side streams start after whatever precedes on this stream
+                ev_start.record(torch.cuda.current_stream())
+                vs[j].wait_event(ev_start)
+            with torch.cuda.stream(vs[j]):
+                graphs[j]()
+                ev_done[j].record(vs[j])
+
+        def tail_2s():                                       # the timed region ends when both streams have drained
+            cur = torch.cuda.current_stream()
+            for j in range(2):
+                cur.wait_event(ev_done[j])
+            vcount[0] = 0
+
+        for _ in range(4):
+            step_2s()
+        tail_2s()
+        value_forms["two_stream"] = timed(step_2s, args.steps, tail_2s)
+        value_form = min(value_forms, key=value_forms.get)
+        ms = value_forms[value_form]
     else:
         ms = ms_eager
+        value_forms, value_form = {"eager": ms}, "eager"
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- whole model from device-resident images (FeatureNet mirror + hot path) ----
@@ -497,6 +529,38 @@ def main_ours(args, wl):
         for _ in range(NBUF + 1):
             step_e2e_2s()
         e2e_forms["two_stream"] = timed(step_e2e_2s, args.steps, e2e_tail_2s)
+    # Third form: every step lives on ONE stream (H2D copy -> whole-model graph -> D2H copies) and consecutive steps alternate
+    # between two streams: the copies, the extractor and the hot paths of two independent reference views overlap freely.
+    if use_graph:
+        fs = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        ev_f = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_fs = torch.cuda.Event()
+        counter3 = [0]
+
+        def step_e2e_alt():
+            i = counter3[0]; counter3[0] += 1
+            j = i & 1
+            if i < 2:
+                ev_fs.record(torch.cuda.current_stream())
+                fs[j].wait_event(ev_fs)
+            with torch.cuda.stream(fs[j]):
+                dbuf[j].copy_(host_in[0], non_blocking=True)
+                out = g_full[j]()
+                host_outs[j][0].copy_(out["depth"], non_blocking=True)
+                host_outs[j][1].copy_(out["photometric_confidence"], non_blocking=True)
+                ev_f[j].record(fs[j])
+
+        def e2e_tail_alt():
+            cur = torch.cuda.current_stream()
+            for j in range(2):
+                cur.wait_event(ev_f[j])
+            counter3[0] = 0
+
+        torch.cuda.synchronize()
+        for _ in range(4):
+            step_e2e_alt()
+        e2e_tail_alt()
+        e2e_forms["alternating"] = timed(step_e2e_alt, args.steps, e2e_tail_alt)
     e2e_form = min(e2e_forms, key=e2e_forms.get)
     ms_e2e = e2e_forms[e2e_form]
 
@@ -553,8 +617,10 @@ def main_ours(args, wl):
         "metric": wl["metric"], "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "strict" else "bf16",
-        "data": "synthetic", "eager_ms_per_step": ms_eager / args.steps,
-        "launch": ("CUDA graph replay of the captured step (mvs_b200.GraphedStep); eager_ms_per_step = the same step issued "
+        "data": "synthetic", "eager_ms_per_step": ms_eager / args.steps, "value_form": value_form,
+        "ms_per_step_by_form": {k: v / args.steps for k, v in value_forms.items()},
+        "launch": ("CUDA graph replay of the captured step (mvs_b200.GraphedStep); value_form 'two_stream' = consecutive steps "
+                   "(independent reference views) alternate on two streams; eager_ms_per_step = the same step issued "
                    "launch by launch from Python, the pass the per-kernel events of `roofline` come from") if use_graph
                   else "eager launches",
         "config": {"workload": wl["name"], "mode": args.mode, "ref_views_per_step": B,
@@ -568,7 +634,9 @@ def main_ours(args, wl):
                 "ms_per_step_by_form": {k: v / args.steps for k, v in e2e_forms.items()},
                 "what": "pinned uint8 images [B,N,3,H,W] -> H2D -> /255 + FeatureNet mirror + hot path -> D2H depth + confidence "
                         "(the reference's model(imgs, proj_matrices, depth_values) boundary)",
-                "note": "input copy of step i+1 and read-back of step i-1 overlap step i on side streams"},
+                "note": "forms: serial = copy stream + one whole-model graph per step + read-back stream; two_stream = the extractor "
+                        "of step i+1 (own graph / stream) under the hot path of step i; alternating = every step (copy in, whole-model "
+                        "graph, copies out) on one of two streams in turn; the copies are inside the timed region in all of them"},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"kernel": f"warp_variance (fused homography warp + variance, {len(per_stage)} launch(es)/step)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
