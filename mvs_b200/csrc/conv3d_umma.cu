@@ -38,6 +38,17 @@
 //     TMEM wait, four accumulators per batch); TMEM double-buffered per step.  <false, 2>: skip layers, 2 CTAs/SM;
 //     <false, 3>: the others, 3 CTAs/SM.
 //
+// Round-2 additions (DESIGN.md 4.2 has the measurements behind each):
+//   * `prob` (Cout = 1) packs one TMEM column per (row tap, step tap) -- N = 16 / 32 MMAs, 8 columns per output row, up to 15
+//     rows per step; Cin = 8 layers pair input rows (three K = 16 steps per two rows, the shared step updates four rows);
+//   * W-de-interleaved skip tensors (MVS_Y_DW / MVS_X_DW / MVS_SKIP_DW): conv0 / 2 / 4 write [even | odd] columns, the stride-2
+//     layers stage contiguous runs, the transposed layers read one run per output parity and store column pairs as 32 bytes;
+//   * 2D layers (the feature extractors): MVS_KD1 (images stacked on the depth axis: only the centre depth tap's MMAs) and the
+//     flat 2D mode MVS_FLAT2D = conv3d_umma_kernel<true, 4 | 5> (a slab is a block of image rows, no step-tap partials, 15
+//     rows per step; <true, 5> adds a pixel-shuffled half-resolution skip operand, MVS_SKIP_PS);
+//   * programmatic dependent launch: everything before `griddepcontrol.wait` (TMEM allocation, barriers, weight staging, index
+//     tables) runs under the tail of the previous kernel in the stream.
+//
 // Lessons that shaped the code (DESIGN.md 4.2 has the measurements): every role is ONE warp running dependent scalar
 // code (~5 clk per instruction), so per-step bookkeeping -- runtime divisions, re-materialised 64-bit index arithmetic,
 // dynamically indexed parameter reads -- is what the pipeline waits for, not bytes or FLOPs; issuing tcgen05.mma from
