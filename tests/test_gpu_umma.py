@@ -80,6 +80,36 @@ def test_conv3d_c8_layer(cin, cout, stride, transposed, dhw):
         np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=4e-3)
 
 
+NOSKIP_LAYERS = [
+    # cin, cout, (D, H, W): stride-1 layers WITHOUT a skip operand (conv0 / prob as CostRegNet runs them; test_conv3d_c8_layer adds one)
+    (8, 8, (3, 5, 40)), (8, 8, (8, 40, 150)), (16, 8, (11, 9, 64)), (16, 8, (32, 13, 130)), (32, 8, (12, 21, 130)),
+    (32, 8, (48, 7, 100)), (8, 1, (4, 6, 133)), (8, 1, (21, 19, 140)), (16, 1, (9, 11, 70)), (8, 8, (1, 9, 30)), (8, 8, (2, 3, 129)),
+]
+
+
+@pytest.mark.parametrize("cin,cout,dhw", NOSKIP_LAYERS)
+def test_conv3d_c8_stride1_without_skip(cin, cout, dhw):
+    """conv0 / prob shapes against the CPU oracle: odd row counts, row blocks that do not divide D, more steps than TMEM buffers,
+    `prob`'s one-column packing with up to 15 rows per step."""
+    from mvs_b200 import ops
+    rng = np.random.RandomState(100 + cin + cout + dhw[0])
+    D, H, W = dhw
+    x = bf(rng.standard_normal((2, cin, D, H, W)).astype(np.float32))
+    w = bf((rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(27 * cin)).astype(np.float32))
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = (0.3 * rng.standard_normal(cout)).astype(np.float32)
+    ref = O.conv3d(x, w, None, 1, False) * scale.reshape(1, -1, 1, 1, 1) + shift.reshape(1, -1, 1, 1, 1)
+    relu = cout != 1
+    if relu:
+        ref = np.maximum(ref, 0)
+    y = ops.conv3d_c8(ops.pack_c8(cu(x)), ops.pack_conv_weights(cu(w), 1, False), cin, cout, cu(scale), cu(shift), None, 1, False, relu)
+    torch.cuda.synchronize()
+    if cout == 1:
+        np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+    else:
+        np.testing.assert_allclose(ops.unpack_c8(y, cout).cpu().numpy(), ref, rtol=2 ** -7, atol=4e-3)
+
+
 def _dw_perm(W):
     """index list p with natural[..., w] == dw[..., p[w]]: column w sits at (w & 1) * ceil(W / 2) + (w >> 1)."""
     w = torch.arange(W)
