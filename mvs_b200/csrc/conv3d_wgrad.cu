@@ -23,8 +23,8 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
 {
     constexpr int TW = S * WG_SEG + 2;                 // staged T positions per row: s*w + kw - 1 for w < 64, kw < 3
     constexpr int TP = S == 1 ? 72 : 136;              // padded row pitch (pitch mod 32 == 8: conflict-free for 8 b x 4 lanes)
-    __shared__ float sA[8][WG_SEG];
-    __shared__ float sT[8][9][TP];
+    __shared__ __align__(16) float sA[8][WG_SEG];
+    __shared__ __align__(16) float sT[8][9][TP];
     const int tid = threadIdx.x, pair = tid >> 2, lane = tid & 3;
     const int a_loc = pair >> 3, b_loc = pair & 7;
     const int a0 = blockIdx.y * 8, b0 = blockIdx.z * 8;
@@ -57,15 +57,28 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
                 sT[c][r][j] = ok ? __ldg(T + ((size_t)n * Cb + b) * tvol + ((size_t)td * Ht + th) * Wt + tw) : 0.f;
             }
             __syncthreads();
-            const int wn = min(WG_SEG, Wa - w0);
-            for (int w = lane; w < wn; w += 4) {
-                const float av = sA[a_loc][w];
+            // four consecutive positions per lane and trip: the A values and each T row segment come as 16-byte shared-memory
+            // loads (19 / 28 loads per 108 FMAs; one scalar load per FMA made the kernel shared-memory bound).  Positions
+            // beyond the row end carry A = 0 (staged above), so no bound is needed.
+            for (int w = lane * 4; w < WG_SEG; w += 16) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(&sA[a_loc][w]);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
                 for (int r = 0; r < 9; ++r) {
-                    const float *t = &sT[b_loc][r][S * w];
-                    acc[r * 3 + 0] = fmaf(av, t[0], acc[r * 3 + 0]);
-                    acc[r * 3 + 1] = fmaf(av, t[1], acc[r * 3 + 1]);
-                    acc[r * 3 + 2] = fmaf(av, t[2], acc[r * 3 + 2]);
+                    constexpr int NV = (S * 3 + 3 + 3) / 4;                     // float4 loads covering offsets 0 .. S*3 + 2
+                    float tt[NV * 4];
+                    const float4 *t4 = reinterpret_cast<const float4 *>(&sT[b_loc][r][S * w]);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const float4 q = t4[v];
+                        tt[v * 4 + 0] = q.x; tt[v * 4 + 1] = q.y; tt[v * 4 + 2] = q.z; tt[v * 4 + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[r * 3 + 0] = fmaf(av[j], tt[S * j + 0], acc[r * 3 + 0]);
+                        acc[r * 3 + 1] = fmaf(av[j], tt[S * j + 1], acc[r * 3 + 1]);
+                        acc[r * 3 + 2] = fmaf(av[j], tt[S * j + 2], acc[r * 3 + 2]);
+                    }
                 }
             }
         }
