@@ -179,6 +179,21 @@ int mvs_conv3d_fwd(const float *x, const float *w, const float *scale, const flo
 int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, int B, int Cin, int Cout, int D, int H, int W,
                      int stride, int transposed, void *stream);
 
+/* Train-mode BatchNorm3d (+ ReLU) of the conv blocks under training (MVSNet/models/module.py:26-33,
+ * CasMVSNet/models/module.py:139,182; replaces F.batch_norm(training=True) + F.relu and their autograd): full-grid streaming
+ * passes over x [B,C,S] fp32 (S = D*H*W).  sums [2*C] double must be ZERO on entry (atomicAdd).
+ *   mvs_bn_stats      sums[c] = sum x, sums[C+c] = sum x^2
+ *   mvs_bn_apply      y = [relu](x * a[c] + k[c])                          a = invstd*gamma, k = beta - mean*a
+ *   mvs_bn_bwd_stats  sums[c] = sum g, sums[C+c] = sum g*xhat              g = dy * [x*a + k > 0] (relu) | dy
+ *   mvs_bn_bwd_apply  dx = ga[c] * (g - mg[c] - xhat * mgx[c])             ga = gamma*invstd, mg = sum_g/M, mgx = sum_gx/M */
+int mvs_bn_stats(const float *x, double *sums, int B, int C, int64_t S, void *stream);
+int mvs_bn_apply(const float *x, const float *a, const float *k, float *y, int B, int C, int64_t S, int relu, void *stream);
+int mvs_bn_bwd_stats(const float *x, const float *dy, const float *a, const float *k, const float *mean, const float *invstd,
+                     double *sums, int B, int C, int64_t S, int relu, void *stream);
+int mvs_bn_bwd_apply(const float *x, const float *dy, const float *a, const float *k, const float *mean, const float *invstd,
+                     const float *ga, const float *mg, const float *mgx, float *dx, int B, int C, int64_t S, int relu,
+                     void *stream);
+
 /* Fast variant: C8 bf16 activations, tcgen05 (UMMA) implicit GEMM, operands staged in shared memory by the TMA engine
  * (1-D bulk copies per staged line in the stride-1 layers, cp.async in the stride-2 / transposed layers), TMEM
  * accumulators; weights pre-packed by mvs_conv3d_c8_pack_weights.  y is C8 bf16, or fp32

@@ -59,6 +59,10 @@ SIGNATURES = {
     "mvs_border_add_c8h": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
     "mvs_conv3d_fwd": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
     "mvs_conv3d_wgrad": (_i, [_vp] * 3 + [_i] * 8 + [_vp]),
+    "mvs_bn_stats": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
+    "mvs_bn_apply": (_i, [_vp] * 4 + [_i, _i, _i64, _i, _vp]),
+    "mvs_bn_bwd_stats": (_i, [_vp] * 7 + [_i, _i, _i64, _i, _vp]),
+    "mvs_bn_bwd_apply": (_i, [_vp] * 10 + [_i, _i, _i64, _i, _vp]),
     "mvs_conv3d_c8_packed_weight_bytes": (_i64, [_i] * 4),
     "mvs_conv3d_c8_pack_weights": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
     "mvs_conv3d_c8_pack_weights_ex": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),

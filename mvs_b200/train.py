@@ -9,8 +9,9 @@ CVP-MVSNet/train.py:184-219, MVSNet/train.py:204-227), gradients averaged over r
   * 3x3x3 convolutions: forward on `mvs_conv3d_fwd` (strict fp32), data gradient on the SAME kernel -- the data gradient of a
     strided convolution is the transposed convolution with the same weight tensor and vice versa (weight [Cout,Cin,3,3,3] of a
     Conv3d read as the [in,out,3,3,3] weight of a ConvTranspose3d); weight gradient: `mvs_conv3d_wgrad` (strict fp32 SIMT);
-  * train-mode BatchNorm3d (batch statistics + running-stat update) and ReLU stay ATen ops on the conv output
-    (`F.batch_norm(training=True)`): the gap to the fused eval epilogue is stated in DESIGN.md;
+  * train-mode BatchNorm3d (batch statistics + running-stat update) + ReLU: `BnReluFn` on the streaming kernels of
+    csrc/bn_train.cu (two full-grid passes each way; ATen's NCDHW batch-norm kernels run a few CTAs per channel and cost
+    12.7 ms per backward call at the CVP coarse level); `MVS_TRAIN_BN=aten` restores `F.batch_norm` + `F.relu`;
   * softmax over D in ATen, depth regression through ops._DepthRegressionFn (kernel forward, analytic backward);
   * gradient all-reduce: ONE flat bucket (0.34-0.93 M parameters = 1.4-3.7 MB, latency-bound) over NCCL on a side stream,
     averaged over ranks -- `GradBucket`; the reference's DDP buckets the same tensors.
@@ -28,6 +29,9 @@ from . import _lib as L
 from . import ops
 from ._lib import check, lib
 from .ops import _dev, _f32c, _p, _stream
+
+import os
+USE_BN_KERNELS = os.environ.get("MVS_TRAIN_BN", "native") != "aten"        # A/B knob
 
 
 def conv3d_wgrad(x, grad_y, stride=1, transposed=False):
@@ -69,6 +73,72 @@ class Conv3dFn(torch.autograd.Function):
         return gx, gw, None, None
 
 
+class BnReluFn(torch.autograd.Function):
+    """Train-mode BatchNorm3d (+ ReLU) on the repo's streaming kernels (csrc/bn_train.cu): batch statistics with biased variance
+    for the normalisation, running statistics updated like torch (unbiased variance, momentum); analytic backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+        x = x.contiguous()
+        B, C = x.shape[:2]
+        S = x[0, 0].numel()
+        M = B * S
+        L = lib()
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            check(L.mvs_bn_stats(_p(x), _p(sums), B, C, S, _stream()), "mvs_bn_stats")
+        mean = sums[:C] / M
+        var = (sums[C:] / M - mean * mean).clamp_min_(0.0)               # biased, float64
+        invstd = torch.rsqrt(var + eps)
+        if running_mean is not None:
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1 - momentum).add_((var * (M / max(M - 1, 1))).to(running_var.dtype), alpha=momentum)
+        g64 = gamma.detach().double() if gamma is not None else torch.ones(C, dtype=torch.float64, device=x.device)
+        b64 = beta.detach().double() if beta is not None else torch.zeros(C, dtype=torch.float64, device=x.device)
+        a = (invstd * g64).float().contiguous()
+        k = (b64 - mean * invstd * g64).float().contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(L.mvs_bn_apply(_p(x), _p(a), _p(k), _p(y), B, C, S, int(relu), _stream()), "mvs_bn_apply")
+        ctx.save_for_backward(x, a, k, mean.float().contiguous(), invstd.float().contiguous(), (invstd * g64).float().contiguous())
+        ctx.relu, ctx.dims, ctx.has_affine = bool(relu), (B, C, S, M), (gamma is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a, k, mean, invstd, ga = ctx.saved_tensors
+        B, C, S, M = ctx.dims
+        dy = dy.contiguous()
+        L = lib()
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            check(L.mvs_bn_bwd_stats(_p(x), _p(dy), _p(a), _p(k), _p(mean), _p(invstd), _p(sums), B, C, S, int(ctx.relu), _stream()),
+                  "mvs_bn_bwd_stats")
+        mg, mgx = (sums[:C] / M).float().contiguous(), (sums[C:] / M).float().contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                check(L.mvs_bn_bwd_apply(_p(x), _p(dy), _p(a), _p(k), _p(mean), _p(invstd), _p(ga), _p(mg), _p(mgx), _p(dx), B, C, S,
+                                         int(ctx.relu), _stream()), "mvs_bn_bwd_apply")
+        dgamma = sums[C:].float() if (ctx.has_affine[0] and ctx.needs_input_grad[1]) else None
+        dbeta = sums[:C].float() if (ctx.has_affine[1] and ctx.needs_input_grad[2]) else None
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def bn_relu_train(x, bn, relu):
+    """Batch-statistics BatchNorm3d (+ ReLU) of a conv block: the repo's kernels on CUDA fp32 tensors, ATen otherwise."""
+    if x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and USE_BN_KERNELS:
+        y = BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
+                           bn.running_var if bn.track_running_stats else None, bn.momentum, bn.eps, relu)
+    else:
+        y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+        if relu:
+            y = F.relu(y)
+    return y
+
+
 def train_layer(x, weight, bn, stride, transposed, relu, skip):
     """Conv3d / ConvTranspose3d + BatchNorm3d (batch statistics, running stats updated) + ReLU [+ skip], the training
     branch of MVSNet/models/module.py:26-33, CasMVSNet/models/module.py:115-200."""
@@ -76,10 +146,10 @@ def train_layer(x, weight, bn, stride, transposed, relu, skip):
     if bn is not None:
         if bn.momentum is None:
             raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not used by the reference")
-        y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+        y = bn_relu_train(y, bn, relu)
         if bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
-    if relu:
+    elif relu:
         y = F.relu(y)
     return y if skip is None else skip + y
 

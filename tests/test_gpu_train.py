@@ -182,3 +182,31 @@ def test_cvp_network_training_loss_and_gradients_vs_reference_ops():
             np.testing.assert_allclose(p.grad.cpu().numpy(), g.cpu().numpy(), rtol=2e-2, atol=2e-3 * max(s, 1e-8), err_msg=name)
         n += 1
     assert n == 50
+
+
+@pytest.mark.parametrize("shape,relu", [((2, 8, 5, 17, 33), True), ((1, 16, 3, 40, 50), False), ((3, 4, 2, 9, 700), True)])
+def test_bn_relu_train_kernels_vs_aten(shape, relu):
+    """csrc/bn_train.cu behind train.BnReluFn: output, running statistics and all three gradients against
+    F.batch_norm(training=True) [+ F.relu] under torch autograd (fp32; sums in different orders)."""
+    from mvs_b200 import train
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(shape, generator=g) * 1.7 + 0.3).to(DEV).requires_grad_(True)
+    C = shape[1]
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.2).to(DEV).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    rm2, rv2 = rm.clone(), rv.clone()
+    y = train.BnReluFn.apply(x, gamma, beta, rm, rv, 0.1, 1e-5, relu)
+    x2, g2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, gamma, beta))
+    yr = F.batch_norm(x2, rm2, rv2, g2, b2, True, 0.1, 1e-5)
+    if relu:
+        yr = F.relu(yr)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().cpu().numpy(), rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(rm.cpu().numpy(), rm2.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rv.cpu().numpy(), rv2.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    up = torch.randn(shape, generator=g).to(DEV)
+    y.backward(up)
+    yr.backward(up)
+    for a, b, name in ((x.grad, x2.grad, "dx"), (gamma.grad, g2.grad, "dgamma"), (beta.grad, b2.grad, "dbeta")):
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-6, name
