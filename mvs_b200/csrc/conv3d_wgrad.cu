@@ -16,24 +16,29 @@ namespace mvs {
 
 constexpr int WG_SEG = 64;
 
-template <int S>
+// NA = a-channels per thread (a_loc, a_loc + 8, ...): the CTA owns an (8 NA) x 8 block of pairs, and every staged T row
+// segment / shared-memory T load feeds NA times the FMAs (the 8 x 8 version moved 21 KB through L2 per 110 k FMAs and was
+// bound by that)
+template <int S, int NA>
 __global__ void __launch_bounds__(256)
 conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, float *__restrict__ G, int N, int Ca, int Cb,
                     int Da, int Ha, int Wa, int Dt, int Ht, int Wt, int rows_per_cta)
 {
     constexpr int TW = S * WG_SEG + 2;                 // staged T positions per row: s*w + kw - 1 for w < 64, kw < 3
     constexpr int TP = S == 1 ? 72 : 136;              // padded row pitch (pitch mod 32 == 8: conflict-free for 8 b x 4 lanes)
-    __shared__ __align__(16) float sA[8][WG_SEG];
+    __shared__ __align__(16) float sA[8 * NA][WG_SEG];
     __shared__ __align__(16) float sT[8][9][TP];
     const int tid = threadIdx.x, pair = tid >> 2, lane = tid & 3;
     const int a_loc = pair >> 3, b_loc = pair & 7;
-    const int a0 = blockIdx.y * 8, b0 = blockIdx.z * 8;
+    const int a0 = blockIdx.y * 8 * NA, b0 = blockIdx.z * 8;
     const long long total_rows = (long long)N * Da * Ha;
     const long long row_begin = (long long)blockIdx.x * rows_per_cta;
     const long long row_end = min(row_begin + rows_per_cta, total_rows);
-    float acc[27];
+    float acc[NA][27];
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    for (int u = 0; u < NA; ++u)
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc[u][k] = 0.f;
     const size_t avol = (size_t)Da * Ha * Wa, tvol = (size_t)Dt * Ht * Wt;
 
     for (long long row = row_begin; row < row_end; ++row) {
@@ -42,8 +47,8 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
         const int n = (int)(row / ((long long)Ha * Da));
         for (int w0 = 0; w0 < Wa; w0 += WG_SEG) {
             __syncthreads();
-            // A segment: 8 channels x 64 positions
-            for (int i = tid; i < 8 * WG_SEG; i += 256) {
+            // A segment: 8 NA channels x 64 positions
+            for (int i = tid; i < 8 * NA * WG_SEG; i += 256) {
                 const int c = i / WG_SEG, w = i % WG_SEG;
                 const int a = a0 + c;
                 sA[c][w] = (a < Ca && w0 + w < Wa) ? __ldg(A + ((size_t)n * Ca + a) * avol + ((size_t)d * Ha + h) * Wa + w0 + w) : 0.f;
@@ -61,8 +66,12 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
             // loads (19 / 28 loads per 108 FMAs; one scalar load per FMA made the kernel shared-memory bound).  Positions
             // beyond the row end carry A = 0 (staged above), so no bound is needed.
             for (int w = lane * 4; w < WG_SEG; w += 16) {
-                const float4 a4 = *reinterpret_cast<const float4 *>(&sA[a_loc][w]);
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                float av[NA][4];
+#pragma unroll
+                for (int u = 0; u < NA; ++u) {
+                    const float4 a4 = *reinterpret_cast<const float4 *>(&sA[a_loc + 8 * u][w]);
+                    av[u][0] = a4.x; av[u][1] = a4.y; av[u][2] = a4.z; av[u][3] = a4.w;
+                }
 #pragma unroll
                 for (int r = 0; r < 9; ++r) {
                     constexpr int NV = (S * 3 + 3 + 3) / 4;                     // float4 loads covering offsets 0 .. S*3 + 2
@@ -74,27 +83,32 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
                         tt[v * 4 + 0] = q.x; tt[v * 4 + 1] = q.y; tt[v * 4 + 2] = q.z; tt[v * 4 + 3] = q.w;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc[r * 3 + 0] = fmaf(av[j], tt[S * j + 0], acc[r * 3 + 0]);
-                        acc[r * 3 + 1] = fmaf(av[j], tt[S * j + 1], acc[r * 3 + 1]);
-                        acc[r * 3 + 2] = fmaf(av[j], tt[S * j + 2], acc[r * 3 + 2]);
-                    }
+                    for (int u = 0; u < NA; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[u][r * 3 + 0] = fmaf(av[u][j], tt[S * j + 0], acc[u][r * 3 + 0]);
+                            acc[u][r * 3 + 1] = fmaf(av[u][j], tt[S * j + 1], acc[u][r * 3 + 1]);
+                            acc[u][r * 3 + 2] = fmaf(av[u][j], tt[S * j + 2], acc[u][r * 3 + 2]);
+                        }
                 }
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        float v = acc[k];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        acc[k] = v;
-    }
-    const int a = a0 + a_loc, b = b0 + b_loc;
-    if (lane == 0 && a < Ca && b < Cb) {
-        float *g = G + ((size_t)a * Cb + b) * 27;
+    for (int u = 0; u < NA; ++u) {
 #pragma unroll
-        for (int k = 0; k < 27; ++k) atomicAdd(g + k, acc[k]);
+        for (int k = 0; k < 27; ++k) {
+            float v = acc[u][k];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            acc[u][k] = v;
+        }
+        const int a = a0 + a_loc + 8 * u, b = b0 + b_loc;
+        if (lane == 0 && a < Ca && b < Cb) {
+            float *g = G + ((size_t)a * Cb + b) * 27;
+#pragma unroll
+            for (int k = 0; k < 27; ++k) atomicAdd(g + k, acc[u][k]);
+        }
     }
 }
 
@@ -119,18 +133,19 @@ extern "C" int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, 
     const int Da = transposed ? D : Do, Ha = transposed ? H : Ho, Wa = transposed ? W : Wo;
     const int Dt = transposed ? Do : D, Ht = transposed ? Ho : H, Wt = transposed ? Wo : W;
     const long long rows = (long long)B * Da * Ha;
-    const int pair_blocks = cdiv(Ca, 8) * cdiv(Cb, 8);
+    const int na = Ca > 8 ? 2 : 1;                    // a-channels per thread
+    const int pair_blocks = cdiv(Ca, 8 * na) * cdiv(Cb, 8);
     // ~16 CTAs per SM in total: enough parallelism, few enough CTAs that the final atomics stay cheap
     long long chunks = (16LL * sm_count() + pair_blocks - 1) / pair_blocks;
     if (chunks > rows) chunks = rows;
     if (chunks < 1) chunks = 1;
     const int rows_per_cta = (int)((rows + chunks - 1) / chunks);
-    dim3 grid((unsigned)cdiv(rows, rows_per_cta), cdiv(Ca, 8), cdiv(Cb, 8));
+    dim3 grid((unsigned)cdiv(rows, rows_per_cta), cdiv(Ca, 8 * na), cdiv(Cb, 8));
     MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "too many channel blocks");
     cudaStream_t st = (cudaStream_t)stream;
-    if (stride == 1)
-        conv3d_wgrad_kernel<1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
-    else
-        conv3d_wgrad_kernel<2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    if (stride == 1 && na == 2) conv3d_wgrad_kernel<1, 2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    else if (stride == 1) conv3d_wgrad_kernel<1, 1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    else if (na == 2) conv3d_wgrad_kernel<2, 2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    else conv3d_wgrad_kernel<2, 1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
     return check_launch("mvs_conv3d_wgrad");
 }
