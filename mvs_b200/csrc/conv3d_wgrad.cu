@@ -5,11 +5,13 @@
 // Replaces the wgrad half of autograd through nn.Conv3d / nn.ConvTranspose3d (CasMVSNet/models/module.py:137,180,
 // MVSNet/models/module.py:29, CVP-MVSNet/models/net.py:56-76) under loss.backward() (CasMVSNet/train.py:165-170).
 //
-// A CTA owns an 8 x 8 block of (a, b) channel pairs and a contiguous chunk of A's (n, d, h) rows; it walks the rows in
+// A CTA owns an (8 NA) x 8 block of (a, b) channel pairs (NA = 1, 2 or 4 a-channels per thread) and a contiguous chunk of A's (n, d, h) rows; it walks the rows in
 // 64-position W segments, staging the A segment and the nine (kd, kh) T rows (with their kw halo) in shared memory.
 // Thread = (pair, lane of 4): 27 accumulators in registers over positions w = lane, lane + 4, ...; at the end the four
 // lanes are reduced by shuffles and the CTA adds its 64 x 27 partial sums to gw with atomicAdd (the accumulation order
 // over CTAs is therefore not deterministic in the last bits, like cuDNN's default wgrad algorithms).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mvs {
@@ -133,7 +135,8 @@ extern "C" int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, 
     const int Da = transposed ? D : Do, Ha = transposed ? H : Ho, Wa = transposed ? W : Wo;
     const int Dt = transposed ? Do : D, Ht = transposed ? Ho : H, Wt = transposed ? Wo : W;
     const long long rows = (long long)B * Da * Ha;
-    const int na = Ca > 8 ? 2 : 1;                    // a-channels per thread
+    static const int na_max = getenv("MVS_WGRAD_NA") ? atoi(getenv("MVS_WGRAD_NA")) : 4;      // tuning knob
+    const int na = (Ca >= 32 && na_max >= 4) ? 4 : (Ca > 8 && na_max >= 2 ? 2 : 1);           // a-channels per thread
     const int pair_blocks = cdiv(Ca, 8 * na) * cdiv(Cb, 8);
     // ~16 CTAs per SM in total: enough parallelism, few enough CTAs that the final atomics stay cheap
     long long chunks = (16LL * sm_count() + pair_blocks - 1) / pair_blocks;
@@ -143,7 +146,9 @@ extern "C" int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, 
     dim3 grid((unsigned)cdiv(rows, rows_per_cta), cdiv(Ca, 8 * na), cdiv(Cb, 8));
     MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "too many channel blocks");
     cudaStream_t st = (cudaStream_t)stream;
-    if (stride == 1 && na == 2) conv3d_wgrad_kernel<1, 2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    if (stride == 1 && na == 4) conv3d_wgrad_kernel<1, 4><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    else if (stride == 2 && na == 4) conv3d_wgrad_kernel<2, 4><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    else if (stride == 1 && na == 2) conv3d_wgrad_kernel<1, 2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
     else if (stride == 1) conv3d_wgrad_kernel<1, 1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
     else if (na == 2) conv3d_wgrad_kernel<2, 2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
     else conv3d_wgrad_kernel<2, 1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
