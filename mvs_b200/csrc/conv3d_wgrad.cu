@@ -11,6 +11,7 @@
 // lanes are reduced by shuffles and the CTA adds its 64 x 27 partial sums to gw with atomicAdd (the accumulation order
 // over CTAs is therefore not deterministic in the last bits, like cuDNN's default wgrad algorithms).
 #include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 
@@ -28,8 +29,11 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
 {
     constexpr int TW = S * WG_SEG + 2;                 // staged T positions per row: s*w + kw - 1 for w < 64, kw < 3
     constexpr int TP = S == 1 ? 72 : 136;              // padded row pitch (pitch mod 32 == 8: conflict-free for 8 b x 4 lanes)
-    __shared__ __align__(16) float sA[8 * NA][WG_SEG];
-    __shared__ __align__(16) float sT[8][9][TP];
+    // two stages: the segment q + 1 is fetched with cp.async while segment q is multiplied (staged synchronously, the loads'
+    // latency was exposed once per segment -- about half of the kernel's time)
+    extern __shared__ __align__(16) float smem_wg[];
+    float (*sA)[8 * NA][WG_SEG] = reinterpret_cast<float (*)[8 * NA][WG_SEG]>(smem_wg);
+    float (*sT)[8][9][TP] = reinterpret_cast<float (*)[8][9][TP]>(smem_wg + 2 * 8 * NA * WG_SEG);
     const int tid = threadIdx.x, pair = tid >> 2, lane = tid & 3;
     const int a_loc = pair >> 3, b_loc = pair & 7;
     const int a0 = blockIdx.y * 8 * NA, b0 = blockIdx.z * 8;
@@ -43,25 +47,44 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
         for (int k = 0; k < 27; ++k) acc[u][k] = 0.f;
     const size_t avol = (size_t)Da * Ha * Wa, tvol = (size_t)Dt * Ht * Wt;
 
-    for (long long row = row_begin; row < row_end; ++row) {
+    const int nseg = (Wa + WG_SEG - 1) / WG_SEG;
+    const long long n_q = (row_end - row_begin) * nseg;        // (row, segment) work items of this CTA
+    auto stage = [&](int buf, long long q) {
+        const long long row = row_begin + q / nseg;
+        const int w0 = (int)(q % nseg) * WG_SEG;
         const int h = (int)(row % Ha);
         const int d = (int)((row / Ha) % Da);
         const int n = (int)(row / ((long long)Ha * Da));
-        for (int w0 = 0; w0 < Wa; w0 += WG_SEG) {
-            __syncthreads();
-            // A segment: 8 NA channels x 64 positions
-            for (int i = tid; i < 8 * NA * WG_SEG; i += 256) {
-                const int c = i / WG_SEG, w = i % WG_SEG;
-                const int a = a0 + c;
-                sA[c][w] = (a < Ca && w0 + w < Wa) ? __ldg(A + ((size_t)n * Ca + a) * avol + ((size_t)d * Ha + h) * Wa + w0 + w) : 0.f;
-            }
-            // T rows: 8 channels x 9 (kd, kh) rows x (S*64 + 2) positions starting at S*w0 - 1
-            for (int i = tid; i < 8 * 9 * TW; i += 256) {
-                const int j = i % TW, r = (i / TW) % 9, c = i / (TW * 9);
-                const int b = b0 + c;
-                const int td = S * d + r / 3 - 1, th = S * h + r % 3 - 1, tw = S * w0 - 1 + j;
-                const bool ok = b < Cb && td >= 0 && td < Dt && th >= 0 && th < Ht && tw >= 0 && tw < Wt;
-                sT[c][r][j] = ok ? __ldg(T + ((size_t)n * Cb + b) * tvol + ((size_t)td * Ht + th) * Wt + tw) : 0.f;
+        // A segment: 8 NA channels x 64 positions (zero beyond the channels / the row end: 0-byte copies zero-fill)
+        for (int i = tid; i < 8 * NA * WG_SEG; i += 256) {
+            const int c = i / WG_SEG, w = i % WG_SEG;
+            const int a = a0 + c;
+            const bool ok = a < Ca && w0 + w < Wa;
+            const float *src = ok ? A + ((size_t)n * Ca + a) * avol + ((size_t)d * Ha + h) * Wa + w0 + w : A;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(&sA[buf][c][w])), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+        }
+        // T rows: 8 channels x 9 (kd, kh) rows x (S*64 + 2) positions starting at S*w0 - 1
+        for (int i = tid; i < 8 * 9 * TW; i += 256) {
+            const int j = i % TW, r = (i / TW) % 9, c = i / (TW * 9);
+            const int b = b0 + c;
+            const int td = S * d + r / 3 - 1, th = S * h + r % 3 - 1, tw = S * w0 - 1 + j;
+            const bool ok = b < Cb && td >= 0 && td < Dt && th >= 0 && th < Ht && tw >= 0 && tw < Wt;
+            const float *src = ok ? T + ((size_t)n * Cb + b) * tvol + ((size_t)td * Ht + th) * Wt + tw : T;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(&sT[buf][c][r][j])), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (n_q > 0) stage(0, 0);
+    for (long long q = 0; q < n_q; ++q) {
+        {
+            const int buf = (int)(q & 1);
+            if (q + 1 < n_q) {
+                stage(buf ^ 1, q + 1);
+                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             }
             __syncthreads();
             // four consecutive positions per lane and trip: the A values and each T row segment come as 16-byte shared-memory
@@ -71,18 +94,18 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
                 float av[NA][4];
 #pragma unroll
                 for (int u = 0; u < NA; ++u) {
-                    const float4 a4 = *reinterpret_cast<const float4 *>(&sA[a_loc + 8 * u][w]);
+                    const float4 a4 = *reinterpret_cast<const float4 *>(&sA[buf][a_loc + 8 * u][w]);
                     av[u][0] = a4.x; av[u][1] = a4.y; av[u][2] = a4.z; av[u][3] = a4.w;
                 }
 #pragma unroll
                 for (int r = 0; r < 9; ++r) {
                     constexpr int NV = (S * 3 + 3 + 3) / 4;                     // float4 loads covering offsets 0 .. S*3 + 2
                     float tt[NV * 4];
-                    const float4 *t4 = reinterpret_cast<const float4 *>(&sT[b_loc][r][S * w]);
+                    const float4 *t4 = reinterpret_cast<const float4 *>(&sT[buf][b_loc][r][S * w]);
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        const float4 q = t4[v];
-                        tt[v * 4 + 0] = q.x; tt[v * 4 + 1] = q.y; tt[v * 4 + 2] = q.z; tt[v * 4 + 3] = q.w;
+                        const float4 q4 = t4[v];
+                        tt[v * 4 + 0] = q4.x; tt[v * 4 + 1] = q4.y; tt[v * 4 + 2] = q4.z; tt[v * 4 + 3] = q4.w;
                     }
 #pragma unroll
                     for (int u = 0; u < NA; ++u)
@@ -94,6 +117,7 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
                         }
                 }
             }
+            __syncthreads();            // everyone is done with this stage before the next iteration refills the other one
         }
     }
 #pragma unroll
@@ -146,11 +170,17 @@ extern "C" int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, 
     dim3 grid((unsigned)cdiv(rows, rows_per_cta), cdiv(Ca, 8 * na), cdiv(Cb, 8));
     MVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "too many channel blocks");
     cudaStream_t st = (cudaStream_t)stream;
-    if (stride == 1 && na == 4) conv3d_wgrad_kernel<1, 4><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
-    else if (stride == 2 && na == 4) conv3d_wgrad_kernel<2, 4><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
-    else if (stride == 1 && na == 2) conv3d_wgrad_kernel<1, 2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
-    else if (stride == 1) conv3d_wgrad_kernel<1, 1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
-    else if (na == 2) conv3d_wgrad_kernel<2, 2><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
-    else conv3d_wgrad_kernel<2, 1><<<grid, 256, 0, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+    auto launch = [&](auto kernel, int S_, int NA_) -> cudaError_t {
+        const int tp = S_ == 1 ? 72 : 136;
+        const size_t smem = (size_t)(2 * 8 * NA_ * WG_SEG + 2 * 8 * 9 * tp) * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, 256, smem, st>>>(A, T, gw, B, Ca, Cb, Da, Ha, Wa, Dt, Ht, Wt, rows_per_cta);
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    if (stride == 1) e = na == 4 ? launch(conv3d_wgrad_kernel<1, 4>, 1, 4) : (na == 2 ? launch(conv3d_wgrad_kernel<1, 2>, 1, 2) : launch(conv3d_wgrad_kernel<1, 1>, 1, 1));
+    else e = na == 4 ? launch(conv3d_wgrad_kernel<2, 4>, 2, 4) : (na == 2 ? launch(conv3d_wgrad_kernel<2, 2>, 2, 2) : launch(conv3d_wgrad_kernel<2, 1>, 2, 1));
+    if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     return check_launch("mvs_conv3d_wgrad");
 }
