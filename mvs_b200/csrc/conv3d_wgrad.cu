@@ -22,7 +22,9 @@ constexpr int WG_SEG = 64;
 // NA = a-channels per thread (a_loc, a_loc + 8, ...): the CTA owns an (8 NA) x 8 block of pairs, and every staged T row
 // segment / shared-memory T load feeds NA times the FMAs (the 8 x 8 version moved 21 KB through L2 per 110 k FMAs and was
 // bound by that)
-template <int S, int NA>
+// ONE_A: Ca == 1 (the `prob` layers' grad_y): the eight a-slots of the pair block would all but one multiply zeros, so the
+// slots 0..3 split the segment's sixteen 4-position chunks among themselves instead (one trip each, four times less work)
+template <int S, int NA, bool ONE_A = false>
 __global__ void __launch_bounds__(256)
 conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, float *__restrict__ G, int N, int Ca, int Cb,
                     int Da, int Ha, int Wa, int Dt, int Ht, int Wt, int rows_per_cta)
@@ -90,11 +92,11 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
             // four consecutive positions per lane and trip: the A values and each T row segment come as 16-byte shared-memory
             // loads (19 / 28 loads per 108 FMAs; one scalar load per FMA made the kernel shared-memory bound).  Positions
             // beyond the row end carry A = 0 (staged above), so no bound is needed.
-            for (int w = lane * 4; w < WG_SEG; w += 16) {
+            for (int w = ONE_A ? (a_loc * 4 + lane) * 4 : lane * 4; w < WG_SEG; w += ONE_A ? WG_SEG : 16) {
                 float av[NA][4];
 #pragma unroll
                 for (int u = 0; u < NA; ++u) {
-                    const float4 a4 = *reinterpret_cast<const float4 *>(&sA[buf][a_loc + 8 * u][w]);
+                    const float4 a4 = *reinterpret_cast<const float4 *>(&sA[buf][ONE_A ? 0 : a_loc + 8 * u][w]);
                     av[u][0] = a4.x; av[u][1] = a4.y; av[u][2] = a4.z; av[u][3] = a4.w;
                 }
 #pragma unroll
@@ -129,8 +131,8 @@ conv3d_wgrad_kernel(const float *__restrict__ A, const float *__restrict__ T, fl
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             acc[u][k] = v;
         }
-        const int a = a0 + a_loc + 8 * u, b = b0 + b_loc;
-        if (lane == 0 && a < Ca && b < Cb) {
+        const int a = ONE_A ? a0 : a0 + a_loc + 8 * u, b = b0 + b_loc;
+        if (lane == 0 && a < Ca && b < Cb && (!ONE_A || a_loc < 4)) {
             float *g = G + ((size_t)a * Cb + b) * 27;
 #pragma unroll
             for (int k = 0; k < 27; ++k) atomicAdd(g + k, acc[u][k]);
@@ -179,7 +181,8 @@ extern "C" int mvs_conv3d_wgrad(const float *x, const float *grad_y, float *gw, 
         return cudaSuccess;
     };
     cudaError_t e;
-    if (stride == 1) e = na == 4 ? launch(conv3d_wgrad_kernel<1, 4>, 1, 4) : (na == 2 ? launch(conv3d_wgrad_kernel<1, 2>, 1, 2) : launch(conv3d_wgrad_kernel<1, 1>, 1, 1));
+    if (Ca == 1) e = stride == 1 ? launch(conv3d_wgrad_kernel<1, 1, true>, 1, 1) : launch(conv3d_wgrad_kernel<2, 1, true>, 2, 1);
+    else if (stride == 1) e = na == 4 ? launch(conv3d_wgrad_kernel<1, 4>, 1, 4) : (na == 2 ? launch(conv3d_wgrad_kernel<1, 2>, 1, 2) : launch(conv3d_wgrad_kernel<1, 1>, 1, 1));
     else e = na == 4 ? launch(conv3d_wgrad_kernel<2, 4>, 2, 4) : (na == 2 ? launch(conv3d_wgrad_kernel<2, 2>, 2, 2) : launch(conv3d_wgrad_kernel<2, 1>, 2, 1));
     if (e != cudaSuccess) return fail(MVS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     return check_launch("mvs_conv3d_wgrad");
